@@ -1,0 +1,199 @@
+"""Generate golden fixtures by running the UNMODIFIED reference code.
+
+Run in the authoring container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/env_*.npz and tests/golden/buffer_*.npz.  The fixtures are
+committed; nothing at test/bench time reads /root/reference.
+
+Reference pieces executed here:
+  * envs/cacc_env.py  CACCEnv            (imports cleanly)
+  * agents/utils.py   OnPolicyBuffer, MultiAgentOnPolicyBuffer, Scheduler
+    (imported with a stub `tensorflow` module: the file only needs tf.nn.relu
+     as a default argument at import time -- SURVEY 8c)
+"""
+import configparser
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    tf = types.ModuleType('tensorflow')
+    tf.nn = types.SimpleNamespace(relu=None)
+    sys.modules['tensorflow'] = tf
+    if not hasattr(np, 'bool'):
+        np.bool = bool  # reference uses the removed alias (agents/utils.py:759,833)
+    from envs.cacc_env import CACCEnv
+    import agents.utils as au
+    return CACCEnv, au
+
+
+def _cfg(name, **over):
+    cp = configparser.ConfigParser()
+    cp.read(os.path.join(REF, 'config', name))
+    for k, v in over.items():
+        cp['ENV_CONFIG'][k] = str(v)
+    return cp
+
+
+def _actions(kind, T, n, seed=0):
+    if kind == 'const3':
+        return np.full((T, n), 3, dtype=np.int32)
+    if kind == 'const0':
+        return np.zeros((T, n), dtype=np.int32)
+    if kind == 'const1':
+        return np.full((T, n), 1, dtype=np.int32)
+    if kind == 'cyc':
+        t = np.arange(T)[:, None]
+        i = np.arange(n)[None, :]
+        return ((t + i) % 4).astype(np.int32)
+    if kind == 'rand':
+        return np.random.RandomState(seed).randint(0, 4, size=(T, n)).astype(np.int32)
+    raise ValueError(kind)
+
+
+def env_case(CACCEnv, ini, kind, test_mode=False, n_reset=1, **over):
+    cp = _cfg(ini, **over)
+    env = CACCEnv(cp['ENV_CONFIG'])
+    eps = []
+    for ep in range(n_reset):
+        if test_mode:
+            # mimic Trainer.run: a train reset precedes the interleaved test episode
+            env.train_mode = True
+            env.reset()
+            env.train_mode = False
+            ob = env.reset(test_ind=-1)
+        else:
+            ob = env.reset()
+        seed_after = env.seed
+        h0 = np.array(env.hs_cur, dtype=np.float64)
+        v0 = np.array(env.vs_cur, dtype=np.float64)
+        acts = _actions(kind, env.T, env.n_agent, seed=100 + ep)
+        obs = [np.concatenate([np.asarray(o, dtype=np.float64) for o in ob])]
+        rews, dones, greps, hs, vs, us = [], [], [], [], [], []
+        nstep = 0
+        for t in range(env.T):
+            ob, r, d, g = env.step(acts[t])
+            obs.append(np.concatenate([np.asarray(o, dtype=np.float64) for o in ob]))
+            rews.append(np.broadcast_to(np.asarray(r, dtype=np.float64), (env.n_agent,)).copy())
+            dones.append(d)
+            greps.append(g)
+            hs.append(np.array(env.hs_cur)); vs.append(np.array(env.vs_cur)); us.append(np.array(env.us_cur))
+            nstep += 1
+            if d:
+                break
+        eps.append(dict(h0=h0, v0=v0, seed_after=seed_after, acts=acts[:nstep], obs=np.array(obs),
+                        rew=np.array(rews), done=np.array(dones), greward=np.array(greps),
+                        hs=np.array(hs), vs=np.array(vs), us=np.array(us),
+                        v0s=np.array(env.v0s)))
+    out = {}
+    for k, ep in enumerate(eps):
+        for key, val in ep.items():
+            out['ep%d_%s' % (k, key)] = val
+    out['n_ep'] = len(eps)
+    out['ini'] = ini
+    out['kind'] = kind
+    out['test_mode'] = test_mode
+    out['over'] = repr(over)
+    return out
+
+
+def buffer_case(au, alpha, multi=True, T=60, n=8, seed=0):
+    rs = np.random.RandomState(seed)
+    dist = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
+    gamma = 0.99
+    out = {}
+    if multi:
+        buf = au.MultiAgentOnPolicyBuffer(gamma, alpha, dist)
+        rec = dict(r=[], v=[], done=[])
+        for t in range(T):
+            r = rs.randn() if alpha < 0 else rs.randn(n)
+            ob = rs.randn(n, 5); p = rs.rand(n, 4); a = rs.randint(0, 4, n); v = rs.randn(n)
+            done = (t == 29)  # a mid-batch terminal to exercise the (1-done) path
+            buf.add_transition(ob, p, a, r, v, done)
+            rec['r'].append(np.broadcast_to(np.asarray(r, dtype=np.float64), (n,)).copy())
+            rec['v'].append(v); rec['done'].append(done)
+        R_end = rs.randn(n)
+        obs, ps, acts, dones, Rs, Advs = buf.sample_transition(R_end)
+        out.update(obs=obs, ps=ps, acts=acts, dones_pre=dones, Rs=Rs, Advs=Advs, R_end=R_end,
+                   r=np.array(rec['r']), v=np.array(rec['v']), done_post=np.array(rec['done']),
+                   alpha=alpha, gamma=gamma, dist=dist)
+    else:
+        # IA2C: one OnPolicyBuffer per agent (models.py:153-158), shared reward object
+        bufs = [au.OnPolicyBuffer(gamma, alpha, dist[i]) for i in range(n)]
+        rec = dict(r=[], v=[], done=[])
+        for t in range(T):
+            r = rs.randn() if alpha < 0 else rs.randn(n)
+            v = rs.randn(n)
+            done = (t == 29)
+            for i in range(n):
+                bufs[i].add_transition(rs.randn(10), rs.randint(0, 4, 2), rs.randint(0, 4), r, v[i], done)
+            rec['r'].append(np.broadcast_to(np.asarray(r, dtype=np.float64), (n,)).copy())
+            rec['v'].append(v); rec['done'].append(done)
+        R_end = rs.randn(n)
+        Rs, Advs = [], []
+        for i in range(n):
+            _, _, _, dones, R, A = bufs[i].sample_transition(R_end[i])
+            Rs.append(R); Advs.append(A)
+        out.update(Rs=np.array(Rs), Advs=np.array(Advs), R_end=R_end, dones_pre=dones,
+                   r=np.array(rec['r']), v=np.array(rec['v']), done_post=np.array(rec['done']),
+                   alpha=alpha, gamma=gamma, dist=dist)
+    return out
+
+
+def scheduler_case(au):
+    s1 = au.Scheduler(5e-4, decay='constant')
+    s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
+    return dict(const=np.array([s1.get(60) for _ in range(5)]),
+                linear=np.array([s2.get(60) for _ in range(20000)][::997]))
+
+
+def main():
+    CACCEnv, au = _import_reference()
+    cases = [
+        ('env_nc_catchup_const3', ('config_ma2c_nc_catchup.ini', 'const3'), {}),
+        ('env_nc_catchup_cyc', ('config_ma2c_nc_catchup.ini', 'cyc'), {}),
+        ('env_nc_catchup_rand2', ('config_ma2c_nc_catchup.ini', 'rand'), dict(n_reset=2)),
+        ('env_nc_catchup_test', ('config_ma2c_nc_catchup.ini', 'const3'), dict(test_mode=True)),
+        ('env_ic3_slowdown_const3', ('config_ma2c_cnet_slowdown.ini', 'const3'), {}),
+        ('env_ic3_slowdown_cyc', ('config_ma2c_cnet_slowdown.ini', 'cyc'), {}),
+        ('env_ic3_slowdown_const0', ('config_ma2c_cnet_slowdown.ini', 'const0'), {}),
+        ('env_ic3_slowdown_test', ('config_ma2c_cnet_slowdown.ini', 'rand'), dict(test_mode=True)),
+        ('env_ia2c_catchup_rand', ('config_ia2c_catchup.ini', 'rand'), {}),
+        ('env_ia2c_slowdown_coop', ('config_ia2c_slowdown.ini', 'rand'), {}),
+        ('env_dial_catchup_const1', ('config_ma2c_dial_catchup.ini', 'const1'), {}),
+        # (config seed -1 -- the only value reaching the deterministic-init branch at
+        #  cacc_env.py:290/311 -- is rejected by np.random.seed in __init__: dead code)
+        ('env_nc_catchup_seed0', ('config_ma2c_nc_catchup.ini', 'const3'), dict(seed=0)),
+    ]
+    for name, (ini, kind), kw in cases:
+        out = env_case(CACCEnv, ini, kind, **kw)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'steps', len(out['ep0_done']), 'sumG', float(np.sum(out['ep0_greward'])))
+    for name, alpha, multi in [('buffer_ma_global', -1, True), ('buffer_ma_spatial09', 0.9, True),
+                               ('buffer_ia_global', -1, False), ('buffer_ia_spatial08', 0.8, False)]:
+        out = buffer_case(au, alpha, multi)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'sumRs', float(np.sum(out['Rs'])))
+    # exact KAT recipe from SURVEY 8(c): no mid-batch done
+    rs = np.random.RandomState(0)
+    n = 8
+    dist = np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])
+    buf = au.MultiAgentOnPolicyBuffer(0.99, -1, dist)
+    for t in range(60):
+        r = rs.randn(); ob = rs.randn(8, 5); p = rs.rand(8, 4); a = rs.randint(0, 4, 8); v = rs.randn(8)
+        buf.add_transition(ob, p, a, r, v, False)
+    R_end = rs.randn(8)
+    _, _, _, _, Rs, Advs = buf.sample_transition(R_end)
+    print('KAT alpha=-1: Rs[0,:3]', Rs[0, :3], 'Advs[7,-2:]', Advs[7, -2:], 'sumRs', Rs.sum())
+    np.savez_compressed(os.path.join(HERE, 'scheduler.npz'), **scheduler_case(au))
+
+
+if __name__ == '__main__':
+    main()
