@@ -1,0 +1,219 @@
+"""Flat parameter layout + the `nmarl_model` descriptor handed to the kernels.
+
+Variable names, shapes and creation order follow the reference graphs so checkpoints and the
+parity tests can address weights by the reference's own names:
+  NeurComm  nc/lstm_comm_i/{w_msg,b_msg,w_ob,b_ob,w_fp,b_fp,wx_hid,wh_hid,b_hid}  agents/utils.py:141-162
+  CommNet   ic3/lstm_ic3_i/{w_msg,b_msg,w_ob,b_ob,wx_hid,wh_hid,b_hid}           agents/utils.py:361-377
+  DIAL      dial/lstm_comm_i/{...}, dial/mfc_i/{w,b}                               agents/utils.py:535-566
+  IA2C      lstm_i/fc/{w,b}, lstm_i/lstm/{wx,wh,b}                                 agents/policies.py:145-146
+  heads     <scope>/pi_i/{w,b}, <scope>/v_i/{w,b}   (IA2C: lstm_i/pi, lstm_i/v)    agents/policies.py:50-77
+
+In the flat buffer every tensor starts on a 16-byte boundary, one agent's tensors are
+contiguous (IA2C clips/optimises per agent) and wx_hid/wh_hid are adjacent so the LSTM gate
+GEMM sees one [s_dim+64, 256] matrix.
+"""
+import numpy as np
+
+from . import _lib as L
+
+VARIANT_ID = {'ia2c': L.IA2C, 'ma2c_nc': L.NC, 'ma2c_ic3': L.IC3, 'ma2c_dial': L.DIAL}
+SCOPE = {'ma2c_nc': 'nc', 'ma2c_ic3': 'ic3', 'ma2c_dial': 'dial'}
+CELL = {'ma2c_nc': 'lstm_comm', 'ma2c_ic3': 'lstm_ic3', 'ma2c_dial': 'lstm_comm'}
+NH = L.NH
+
+
+def _up4(x):
+    return (int(x) + 3) // 4 * 4
+
+
+def ortho_init(shape, scale=np.sqrt(2)):
+    """Orthogonal init from the GLOBAL NumPy stream (agents/utils.py:10-23): tall matrices get
+    orthonormal columns, wide ones orthonormal rows, times sqrt(2)."""
+    a = np.random.standard_normal(shape)
+    u, _, vt = np.linalg.svd(a, full_matrices=False)
+    q = u if u.shape == tuple(shape) else vt
+    return (scale * q.reshape(shape)).astype(np.float32)
+
+
+class ModelLayout:
+    def __init__(self, variant, n_s_ls, n_a, neighbor_mask, n_h=64, n_fc=64, obs_mode='gather', base_n_s=None):
+        """obs_mode 'gather': the obs buffer holds each agent's OWN features (width base_n_s) and the
+        kernel concatenates own + neighbours' rows (what the MA2C graphs do, and equal to the IA2C
+        env observation).  'concat' (IA2C API mode): rows are the caller's pre-concatenated obs."""
+        if n_h != NH or n_fc != NH:
+            raise ValueError('kernels are specialised for num_lstm = num_fc = 64 (got %d/%d)' % (n_h, n_fc))
+        if variant not in VARIANT_ID:
+            raise ValueError('unsupported agent %r (hot path covers ia2c, ma2c_nc, ma2c_ic3, ma2c_dial)' % variant)
+        self.variant, self.vid = variant, VARIANT_ID[variant]
+        mask = np.asarray(neighbor_mask).astype(int)
+        N = len(mask)
+        if N > L.MAX_AGENT:
+            raise ValueError('n_agent %d > %d' % (N, L.MAX_AGENT))
+        if not 0 < n_a < L.MAX_NA:
+            raise ValueError('n_a %d out of range' % n_a)
+        self.N, self.n_a, self.mask = N, int(n_a), mask
+        self.nbr = [list(map(int, np.where(mask[i] == 1)[0])) for i in range(N)]
+        if max(len(x) for x in self.nbr) > L.MAX_NBR:
+            raise ValueError('more than %d neighbours' % L.MAX_NBR)
+        self.n_s_ls = [int(x) for x in n_s_ls]
+        self.obs_mode = obs_mode
+        if variant == 'ia2c':
+            if obs_mode == 'gather':
+                self.base_n_s = int(base_n_s) if base_n_s else self.n_s_ls[0] // (1 + len(self.nbr[0]))
+                for i in range(N):
+                    assert self.n_s_ls[i] == self.base_n_s * (1 + len(self.nbr[i])), 'IA2C n_s_ls is not own+neighbours'
+            else:
+                self.base_n_s = None
+        else:
+            self.base_n_s = self.n_s_ls[0]
+            assert all(x == self.base_n_s for x in self.n_s_ls), 'MA2C agents must share n_s'
+        self.s_dim = 3 * NH if variant == 'ma2c_nc' else NH
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _kx(self, i):
+        if self.variant == 'ia2c' and self.obs_mode == 'concat':
+            return self.n_s_ls[i]
+        return self.base_n_s * (1 + len(self.nbr[i]))
+
+    def _build(self):
+        N, n_a, v = self.N, self.n_a, self.variant
+        self.entries = []          # (reference name, offset, shape)
+        self.agents_off = []
+        off = 0
+        toff = 0
+
+        def put(name, shape):
+            nonlocal off
+            o = off
+            self.entries.append((name, o, tuple(shape)))
+            off = _up4(off + int(np.prod(shape)))
+            return o
+
+        for i in range(N):
+            nm = len(self.nbr[i])
+            a = dict(p_begin=off)
+            for k in ('o_w_ob', 'o_b_ob', 'o_w_fp', 'o_b_fp', 'o_w_msg', 'o_b_msg', 'o_wxh', 'o_b',
+                      'o_mfc_w', 'o_mfc_b', 'o_pi_w', 'o_pi_b', 'o_v_w', 'o_v_b', 't_wxh', 't_w_msg', 't_mfc'):
+                a[k] = -1
+            kx = self._kx(i)
+            if v == 'ia2c':
+                s = 'lstm_%d' % i
+                a['o_w_ob'] = put(s + '/fc/w', (kx, NH)); a['o_b_ob'] = put(s + '/fc/b', (NH,))
+                a['o_wxh'] = put(s + '/lstm/wx', (NH, 4 * NH))
+                o2 = put(s + '/lstm/wh', (NH, 4 * NH)); assert o2 == a['o_wxh'] + NH * 4 * NH
+                a['o_b'] = put(s + '/lstm/b', (4 * NH,))
+                hp, hv = s + '/pi', s + '/v'
+            else:
+                s = '%s/%s_%d' % (SCOPE[v], CELL[v], i)
+                km = NH if v == 'ma2c_ic3' else NH * nm
+                a['o_w_msg'] = put(s + '/w_msg', (km, NH)); a['o_b_msg'] = put(s + '/b_msg', (NH,))
+                a['o_w_ob'] = put(s + '/w_ob', (kx, NH)); a['o_b_ob'] = put(s + '/b_ob', (NH,))
+                if v == 'ma2c_nc':
+                    a['o_w_fp'] = put(s + '/w_fp', (n_a * nm, NH)); a['o_b_fp'] = put(s + '/b_fp', (NH,))
+                a['o_wxh'] = put(s + '/wx_hid', (self.s_dim, 4 * NH))
+                o2 = put(s + '/wh_hid', (NH, 4 * NH)); assert o2 == a['o_wxh'] + self.s_dim * 4 * NH
+                a['o_b'] = put(s + '/b_hid', (4 * NH,))
+                if v == 'ma2c_dial':
+                    a['o_mfc_w'] = put('dial/mfc_%d/w' % i, (NH, NH)); a['o_mfc_b'] = put('dial/mfc_%d/b' % i, (NH,))
+                hp, hv = '%s/pi_%d' % (SCOPE[v], i), '%s/v_%d' % (SCOPE[v], i)
+                a['t_w_msg'] = toff; toff += _up4(NH * km)
+                if v == 'ma2c_dial':
+                    a['t_mfc'] = toff; toff += NH * NH
+            a['o_pi_w'] = put(hp + '/w', (NH, n_a)); a['o_pi_b'] = put(hp + '/b', (n_a,))
+            a['o_v_w'] = put(hv + '/w', (NH + n_a * nm, 1)); a['o_v_b'] = put(hv + '/b', (1,))
+            a['t_wxh'] = toff; toff += 4 * NH * (self.s_dim + NH)
+            a['p_end'] = off
+            self.agents_off.append(a)
+        self.n_param, self.n_wt = off, max(toff, 4)
+        self.kx_pad = _up4(max(self._kx(i) for i in range(N)))
+        max_nbr = max(len(x) for x in self.nbr)
+        self.kp_pad = _up4(n_a * max_nbr) if v == 'ma2c_nc' else 0
+        self.km_pad = {'ia2c': 0, 'ma2c_ic3': NH}.get(v, NH * max_nbr)
+        self.ld_in = self.kx_pad + self.kp_pad + self.km_pad
+        if v == 'ia2c' and self.obs_mode == 'concat':
+            self.obs_stride = _up4(max(self.n_s_ls))
+        else:
+            self.obs_stride = _up4(self.base_n_s)
+        self.by_name = {n: (o, s) for n, o, s in self.entries}
+
+    def c_model(self):
+        m = L.Model()
+        m.variant, m.n_agent, m.n_a, m.s_dim = self.vid, self.N, self.n_a, self.s_dim
+        m.obs_stride, m.kx_pad, m.kp_pad, m.km_pad = self.obs_stride, self.kx_pad, self.kp_pad, self.km_pad
+        m.n_param, m.n_wt = self.n_param, self.n_wt
+        m.per_agent_norm = 1 if self.variant == 'ia2c' else 0
+        recv = [[] for _ in range(self.N)]
+        for k in range(self.N):
+            for slot, j in enumerate(self.nbr[k]):
+                recv[j].append((k, slot))
+        for i in range(self.N):
+            ag = m.agent[i]
+            ag.n_nbr = len(self.nbr[i])
+            for s, j in enumerate(self.nbr[i]):
+                ag.nbr[s] = j
+            if len(recv[i]) > L.MAX_NBR:
+                raise ValueError('agent %d is a neighbour of more than %d agents' % (i, L.MAX_NBR))
+            ag.n_recv = len(recv[i])
+            for s, (k, slot) in enumerate(recv[i]):
+                ag.recv_agent[s], ag.recv_slot[s] = k, slot
+            if self.variant == 'ia2c' and self.obs_mode == 'concat':
+                ag.x_nsrc, ag.x_w = 1, self.n_s_ls[i]
+                ag.x_src[0] = i
+            else:
+                srcs = [i] + self.nbr[i]
+                ag.x_nsrc, ag.x_w = len(srcs), self.base_n_s
+                for s, j in enumerate(srcs):
+                    ag.x_src[s] = j
+            for k, val in self.agents_off[i].items():
+                setattr(ag, k, val)
+        return m
+
+    # ---- host-side packing -----------------------------------------------------------------------
+    def init_flat(self):
+        """Reference initialisation order: consumes np.random like graph construction."""
+        params = {}
+        for name, shape in self.creation_order():
+            params[name] = ortho_init(shape) if len(shape) == 2 else np.zeros(shape, dtype=np.float32)
+        return self.pack(params)
+
+    def creation_order(self):
+        """(name, shape) in tf.get_variable order: cells for all agents, (DIAL: mfc), then heads;
+        IA2C agent by agent."""
+        v, N = self.variant, self.N
+        shapes = {n: s for n, _, s in self.entries}
+        order = []
+        if v == 'ia2c':
+            for i in range(N):
+                s = 'lstm_%d' % i
+                order += [s + '/fc/w', s + '/fc/b', s + '/lstm/wx', s + '/lstm/wh', s + '/lstm/b',
+                          s + '/pi/w', s + '/pi/b', s + '/v/w', s + '/v/b']
+        else:
+            for i in range(N):
+                s = '%s/%s_%d' % (SCOPE[v], CELL[v], i)
+                order += [s + '/w_msg', s + '/b_msg', s + '/w_ob', s + '/b_ob']
+                if v == 'ma2c_nc':
+                    order += [s + '/w_fp', s + '/b_fp']
+                order += [s + '/wx_hid', s + '/wh_hid', s + '/b_hid']
+            if v == 'ma2c_dial':
+                for i in range(N):
+                    order += ['dial/mfc_%d/w' % i, 'dial/mfc_%d/b' % i]
+            for i in range(N):
+                sc = SCOPE[v]
+                order += ['%s/pi_%d/w' % (sc, i), '%s/pi_%d/b' % (sc, i), '%s/v_%d/w' % (sc, i), '%s/v_%d/b' % (sc, i)]
+        return [(n, shapes[n]) for n in order]
+
+    def pack(self, params):
+        flat = np.zeros(self.n_param, dtype=np.float32)
+        for name, o, shape in self.entries:
+            a = np.asarray(params[name], dtype=np.float32)
+            assert a.shape == shape, (name, a.shape, shape)
+            flat[o:o + a.size] = a.ravel()
+        return flat
+
+    def unpack(self, flat):
+        flat = np.asarray(flat)
+        return {name: flat[o:o + int(np.prod(shape))].reshape(shape).copy() for name, o, shape in self.entries}
+
+    def n_real_param(self):
+        return int(sum(np.prod(s) for _, _, s in self.entries))

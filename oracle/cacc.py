@@ -160,7 +160,8 @@ class OracleCACC:
         return out
 
     # ---- episode control ----------------------------------------------------------
-    def reset(self, gui=False, test_ind=-1):
+    def reset(self, gui=False, test_ind=-1, u01=None):
+        """u01 (tests only): use this uniform instead of the np.random.rand() draw."""
         self.cur_episode += 1
         if self.train_mode:
             seed = self.seed
@@ -175,14 +176,14 @@ class OracleCACC:
         h0 = np.ones(n) * self.h_star
         if self.name.startswith('catchup'):
             # NB: tests the already-incremented seed attribute (cacc_env.py:176 vs :290)
-            h0[0] = self.h_star * 2 if not self.seed else self.h_star * (1.5 + np.random.rand())
+            h0[0] = self.h_star * 2 if not self.seed else self.h_star * (1.5 + (np.random.rand() if u01 is None else u01))
             v0 = np.ones(n) * self.v_star
             self.v0s = np.ones(self.T + 1) * self.v_star
         else:
             if not self.seed:
                 v0 = np.ones(n) * 2 * self.v_star
             else:
-                v0 = np.ones(n) * self.v_star * (1.5 + np.random.rand())
+                v0 = np.ones(n) * self.v_star * (1.5 + (np.random.rand() if u01 is None else u01))
             self.v0s = np.ones(self.T + 1) * self.v_star
             dec = np.linspace(v0[0], self.v_star, 300)
             self.v0s[:len(dec)] = dec

@@ -1,0 +1,108 @@
+"""CPU: host logic -- flat parameter layout, model descriptor, and that libnmarl.so loads and
+exports every symbol include/nmarl.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import CFG, ROOT, load_cfg
+from deeprl_network_b200 import _lib as L
+from deeprl_network_b200.envs.cacc_env import chain_masks, grid_masks
+from deeprl_network_b200.layout import ModelLayout
+from oracle import nets
+
+N_PARAM = {'ma2c_nc': 598496, 'ma2c_ic3': 307680, 'ma2c_dial': 365536, 'ia2c': 274400}
+
+
+def _layout(variant, **kw):
+    mask, _ = chain_masks(8)
+    n_s_ls = [5] * 8 if variant != 'ia2c' else [10, 15, 15, 15, 15, 15, 15, 10]
+    return ModelLayout(variant, n_s_ls, 4, mask, **kw), mask, n_s_ls
+
+
+@pytest.mark.parametrize('variant', list(N_PARAM))
+def test_param_counts_and_names_match_reference_graph(variant):
+    lay, mask, n_s_ls = _layout(variant, obs_mode='concat' if variant == 'ia2c' else 'gather')
+    assert lay.n_real_param() == N_PARAM[variant]
+    ref = nets.param_shapes(variant, n_s_ls, 4, mask)
+    assert [n for n, _ in lay.creation_order()] == [n for n, _ in ref]
+    assert dict(lay.creation_order()) == dict(ref)
+    for name, off, shape in lay.entries:
+        assert off % 4 == 0, name            # 16-byte alignment for cp.async / float4
+    for a in lay.agents_off:
+        assert a['p_begin'] < a['p_end'] <= lay.n_param
+
+
+@pytest.mark.parametrize('variant', list(N_PARAM))
+def test_pack_unpack_roundtrip_and_init_order(variant):
+    lay, mask, n_s_ls = _layout(variant, obs_mode='concat' if variant == 'ia2c' else 'gather')
+    np.random.seed(12)
+    flat = lay.init_flat()
+    np.random.seed(12)
+    ref = nets.init_params(variant, n_s_ls, 4, mask)          # oracle consumes np.random in the same order
+    mine = lay.unpack(flat)
+    for k in ref:
+        np.testing.assert_array_equal(mine[k], ref[k])
+    np.testing.assert_array_equal(lay.pack(mine), flat)
+    w = mine[[k for k in mine if k.endswith('wx_hid') or k.endswith('lstm/wx')][0]]
+    np.testing.assert_allclose(w.T @ w if w.shape[0] >= w.shape[1] else w @ w.T, 2 * np.eye(min(w.shape)), atol=1e-4)
+
+
+def test_model_descriptor_chain_and_grid():
+    lay, mask, _ = _layout('ma2c_nc')
+    m = lay.c_model()
+    assert (m.n_agent, m.n_a, m.s_dim, m.kx_pad, m.kp_pad, m.km_pad) == (8, 4, 192, 16, 8, 128)
+    assert list(m.agent[0].nbr)[:1] == [1] and m.agent[0].n_nbr == 1
+    assert list(m.agent[3].nbr)[:2] == [2, 4] and list(m.agent[3].x_src)[:3] == [3, 2, 4]
+    a3 = m.agent[3]            # 3 is slot 1 of agent 2's list [1,3] and slot 0 of agent 4's list [3,5]
+    assert sorted(zip(list(a3.recv_agent)[:2], list(a3.recv_slot)[:2])) == [(2, 1), (4, 0)]
+    gm, gd = grid_masks(5)
+    assert gm.sum(1).tolist().count(2) == 4 and gm.sum(1).tolist().count(3) == 12 and gm.sum(1).tolist().count(4) == 9
+    assert gd.max() == 8 and (gm == gm.T).all()
+    lay2 = ModelLayout('ma2c_nc', [5] * 25, 4, gm)
+    assert lay2.n_real_param() == sum(int(np.prod(s)) for _, s in nets.param_shapes('ma2c_nc', [5] * 25, 4, gm))
+    assert lay2.c_model().km_pad == 256
+
+
+def test_ia2c_gather_and_concat_layouts_share_weights():
+    a, _, _ = _layout('ia2c', obs_mode='concat')
+    b, _, _ = _layout('ia2c', obs_mode='gather')
+    assert [(n, o, s) for n, o, s in a.entries] == [(n, o, s) for n, o, s in b.entries]
+    assert a.c_model().agent[1].x_nsrc == 1 and a.c_model().agent[1].x_w == 15 and a.obs_stride == 16
+    assert b.c_model().agent[1].x_nsrc == 3 and b.c_model().agent[1].x_w == 5 and b.obs_stride == 8
+
+
+def test_unsupported_configurations_fail_loudly():
+    mask, _ = chain_masks(8)
+    with pytest.raises(ValueError):
+        ModelLayout('ia2c_fp', [5] * 8, 4, mask)
+    with pytest.raises(ValueError):
+        ModelLayout('ma2c_nc', [5] * 8, 4, mask, n_h=128)
+
+
+def test_library_loads_and_exports_header_symbols():
+    assert os.path.exists(L.LIB_PATH), 'build libnmarl.so first (python -m deeprl_network_b200.build)'
+    lib = L.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'nmarl.h')).read()
+    declared = set(re.findall(r'\b(nmarl_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.nmarl_version() >= 100
+    assert lib.nmarl_sizeof_model() == ctypes.sizeof(L.Model)
+    lay, _, _ = _layout('ma2c_nc')
+    m = lay.c_model()
+    assert lib.nmarl_ws_floats(ctypes.byref(m), 4096, 60) > 0
+    assert lib.nmarl_loss_tiles(ctypes.byref(m), 4096) == 64
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never import the oracle (it is test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'deeprl_network_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+    assert 'oracle' not in open(os.path.join(ROOT, 'main.py')).read()
