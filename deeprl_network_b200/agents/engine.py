@@ -259,6 +259,7 @@ class PolicyEngine:
                                                 L.stream()), 'nmarl_clip_rmsprop_step')
         self.launches += 2
         self.c_bw.copy_(self.c[self.cur]); self.h_bw.copy_(self.h[self.cur])
+        self._refresh_msg()        # DIAL: cached sender-side messages depend on the updated w_mfc
 
     def update(self, lr):
         self.compute_returns()
