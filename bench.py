@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -34,7 +33,7 @@ N_ENV = 4096
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-env', type=int, default=N_ENV, help='parallel envs per GPU')
@@ -54,6 +53,22 @@ def load_cfg(name, **env_over):
 
 
 # ---- CPU arm: the restated reference trainer (oracle/) on the host cores -----------------------
+def cpu_reference_best(cfg_name, updates):
+    """The reference is single-process with TF's default thread pools; M=1 GEMVs gain nothing from
+    threads, so time it with 1 thread and with all host threads and keep the faster."""
+    import torch
+    n_all = torch.get_num_threads()
+    best = None
+    for nt in sorted({1, n_all}):
+        torch.set_num_threads(nt)
+        v, cores, sample, dt = cpu_reference(cfg_name, updates=max(2, updates // 2), warm_updates=1)
+        r = (v, nt, sample + ', torch threads=%d of %d host cores' % (nt, os.cpu_count()), dt / max(2, updates // 2))
+        if best is None or v > best[0]:
+            best = r
+    torch.set_num_threads(n_all)
+    return best
+
+
 def cpu_reference(cfg_name, updates, warm_updates=1):
     """Times `updates` update cycles (n_step env steps each, B=1, per-agent Python loops, one
     forward per call -- the reference's structure) of the restated reference.  Returns
@@ -87,35 +102,39 @@ def cpu_reference(cfg_name, updates, warm_updates=1):
     return steps * n / dt, cores, '%d update cycles of %d env steps, B=1, %s' % (updates, ag.n_step, cfg_name), dt
 
 
-class ClockSampler(threading.Thread):
+class ClockSampler:
+    """Streams `nvidia-smi -lms 100` while the timed region runs (B200_PROFILING.md clocks line)."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.5)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag = True
-        if not self.samples:
+        if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(s[0]) for s in self.samples)
+        time.sleep(0.2)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ''
+        samples = [[x.strip() for x in l.split(',')] for l in out.strip().splitlines() if l.count(',') >= 5]
+        if not samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in samples)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(sm)}
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith('active') for s in samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(samples[0][1]), 'reasons': reasons, 'samples': len(sm)}
 
 
 def main():
@@ -128,12 +147,12 @@ def main():
         if rank != 0:
             return
         import torch
-        val, cores, sample, dt = cpu_reference(args.config, updates=max(1, args.steps), warm_updates=max(1, min(args.warmup, 2)))
+        val, cores, sample, dt = cpu_reference_best(args.config, updates=max(2, 2 * args.steps))
         cp = load_cfg(args.config)
         T, N = int(cp['MODEL_CONFIG']['batch_size']), int(cp['ENV_CONFIG']['n_vehicle'])
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / max(1, args.steps), 'higher_is_better': True,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.config + ', restated reference (TF unavailable), 1 env x %d agents, CPU' % N},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -251,7 +270,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, dt = cpu_reference(args.config, updates=12, warm_updates=1)
+        v, cores, sample, dt = cpu_reference_best(args.config, updates=16)
         cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                'label': 'restated reference (TF unavailable)', 'seconds': dt}
 

@@ -491,19 +491,43 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __grid_constant__
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) red[part][u][c] = acc[c];
-  // bias sums and one-hot sums: thread e handles one output, strided over rows by 1 (fixed order)
-  float extra = 0.f;
+  // bias sums (8) and one-hot sums (n_nbr x n_a): every thread strides over the rows, then a fixed-order
+  // block reduction (warp shuffle tree + per-warp partials summed in warp order)
+  constexpr int NX = 8 + NMARL_MAX_NBR * NMARL_MAX_NA;
+  float ex[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) ex[c] = 0.f;
   const int n_extra = 8 + ag.n_nbr * k.n_a;
-  if (tid < n_extra) {
-    for (long r = r_begin; r < r_end; ++r) {
-      const long t = r / k.B, b = r - t * k.B;
-      const size_t row = ((size_t)t * k.N + i) * k.B + b;
-      if (tid < 8) extra += k.dlv[row * 8 + tid];
-      else {
-        const int s = (tid - 8) / k.n_a, a = (tid - 8) - s * k.n_a;
-        if (k.act[((size_t)t * k.N + ag.nbr[s]) * k.B + b] == a) extra += k.dlv[row * 8 + k.n_a];
+  for (long r = r_begin + tid; r < r_end; r += 256) {
+    const long t = r / k.B, b = r - t * k.B;
+    const size_t row = ((size_t)t * k.N + i) * k.B + b;
+    const float4 d0 = *reinterpret_cast<const float4*>(k.dlv + row * 8);
+    const float4 d1 = *reinterpret_cast<const float4*>(k.dlv + row * 8 + 4);
+    const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ex[c] += dl[c];
+    const float dv = dl[k.n_a];
+#pragma unroll
+    for (int s = 0; s < NMARL_MAX_NBR; ++s) {
+      if (s < ag.n_nbr) {
+        const int a = k.act[((size_t)t * k.N + ag.nbr[s]) * k.B + b];
+#pragma unroll
+        for (int c = 0; c < NMARL_MAX_NA; ++c) ex[8 + s * NMARL_MAX_NA + c] += (c == a) ? dv : 0.f;
       }
     }
+  }
+  __shared__ float redx[8][NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) {
+    float x = ex[c];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((tid & 31) == 0) redx[tid >> 5][c] = x;
+  }
+  __syncthreads();
+  float extra = 0.f;
+  if (tid < n_extra) {
+    const int src = tid < 8 ? tid : 8 + ((tid - 8) / k.n_a) * NMARL_MAX_NA + (tid - 8) % k.n_a;
+    for (int w2 = 0; w2 < 8; ++w2) extra += redx[w2][src];
   }
   red2[tid] = extra;
   __syncthreads();
@@ -606,6 +630,13 @@ int wgrad_splits(long R) {
   return (int)s;
 }
 
+int head_splits(long R) {
+  long s = R / 1024;
+  if (s < 1) s = 1;
+  if (s > 512) s = 512;
+  return (int)s;
+}
+
 int run_wgrad(const nmarl_model* m, const nmarl_bwd_args* a, int ngrp, const float* A, int lda, int a_col0,
               const float* D, int ldd, int d_col0, const int* Ka, const int* o_w, const int* o_b, cudaStream_t st) {
   WgK k{};
@@ -660,7 +691,7 @@ extern "C" int64_t nmarl_ws_floats(const nmarl_model* m, int B, int T) {
   const int splits = wgrad_splits((long)B * T);
   int64_t gate = (int64_t)splits * m->n_agent * (m->s_dim + NH + 1) * NG;
   int64_t enc = (int64_t)splits * m->n_agent * (m->km_pad + m->kx_pad + 1) * NH;
-  int64_t head = (int64_t)splits * m->n_agent * HEAD_WS;
+  int64_t head = (int64_t)head_splits((long)B * T) * m->n_agent * HEAD_WS;
   int64_t r = gate > enc ? gate : enc;
   return r > head ? r : head;
 }
@@ -792,7 +823,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   }
   {
     HeadK h{};
-    h.N = N; h.B = B; h.T = T; h.splits = wgrad_splits((long)B * T); h.n_a = m->n_a;
+    h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a;
     h.h1 = a->h_seq + nb * NH; h.dlv = a->sv_dlv; h.act = a->act; h.ws = a->ws;
     NMARL_CHECK((int64_t)h.splits * N * HEAD_WS <= a->ws_floats, "head wgrad: workspace too small");
     head_wgrad_kernel<<<dim3(h.splits, N), 256, 0, st>>>(*m, h);
