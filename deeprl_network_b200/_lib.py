@@ -27,13 +27,15 @@ class Agent(C.Structure):
                 ('o_mfc_w', C.c_int32), ('o_mfc_b', C.c_int32),
                 ('o_pi_w', C.c_int32), ('o_pi_b', C.c_int32), ('o_v_w', C.c_int32), ('o_v_b', C.c_int32),
                 ('t_wxh', C.c_int32), ('t_w_msg', C.c_int32), ('t_mfc', C.c_int32),
-                ('p_begin', C.c_int32), ('p_end', C.c_int32)]
+                ('p_begin', C.c_int32), ('p_end', C.c_int32),
+                ('tp_x', C.c_int32), ('tp_p', C.c_int32), ('tp_m', C.c_int32), ('tp_g', C.c_int32), ('tp_mfc', C.c_int32),
+                ('tp_gT', C.c_int32), ('tp_mT', C.c_int32), ('tp_mfcT', C.c_int32)]
 
 
 class Model(C.Structure):
     _fields_ = [('variant', C.c_int32), ('n_agent', C.c_int32), ('n_a', C.c_int32), ('s_dim', C.c_int32),
                 ('obs_stride', C.c_int32), ('kx_pad', C.c_int32), ('kp_pad', C.c_int32), ('km_pad', C.c_int32),
-                ('n_param', C.c_int32), ('n_wt', C.c_int32), ('per_agent_norm', C.c_int32), ('_pad', C.c_int32),
+                ('n_param', C.c_int32), ('n_wt', C.c_int32), ('per_agent_norm', C.c_int32), ('n_wp', C.c_int32),
                 ('agent', Agent * MAX_AGENT)]
 
 
@@ -50,7 +52,7 @@ class FwdArgs(C.Structure):
                 ('c_out', C.c_void_p), ('h_out', C.c_void_p), ('msg_out', C.c_void_p),
                 ('pi', C.c_void_p), ('action', C.c_void_p), ('sample_mode', C.c_int32),
                 ('uniforms', C.c_void_p), ('rng', C.c_void_p), ('rng_offset', C.c_uint64),
-                ('act_in', C.c_void_p), ('v', C.c_void_p)]
+                ('act_in', C.c_void_p), ('v', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p)]
 
 
 class BwdArgs(C.Structure):
@@ -63,13 +65,13 @@ class BwdArgs(C.Structure):
                 ('sv_dlv', C.c_void_p), ('sv_dz', C.c_void_p), ('sv_dpre', C.c_void_p), ('sv_dmp', C.c_void_p),
                 ('dh_rec', C.c_void_p), ('dc_rec', C.c_void_p), ('dmsg', C.c_void_p),
                 ('wt', C.c_void_p), ('ws', C.c_void_p), ('ws_floats', C.c_int64),
-                ('loss_part', C.c_void_p), ('grads', C.c_void_p)]
+                ('loss_part', C.c_void_p), ('grads', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p)]
 
 
 _lib = None
 
 EXPORTS = ['nmarl_last_error', 'nmarl_version', 'nmarl_sizeof_model', 'nmarl_sizeof_agent', 'nmarl_sizeof_cacc_cfg',
-           'nmarl_cacc_reset', 'nmarl_cacc_step', 'nmarl_policy_step_p', 'nmarl_policy_step_v', 'nmarl_dial_msg',
+           'nmarl_cacc_reset', 'nmarl_cacc_step', 'nmarl_pack_weights', 'nmarl_policy_step_p', 'nmarl_policy_step_v', 'nmarl_dial_msg',
            'nmarl_rng_advance', 'nmarl_nstep_return_adv', 'nmarl_loss_tiles', 'nmarl_ws_floats',
            'nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt', 'nmarl_clip_rmsprop_step']
 
@@ -91,6 +93,7 @@ def lib():
     L.nmarl_policy_step_p.argtypes = [C.POINTER(Model), C.POINTER(FwdArgs), P]
     L.nmarl_policy_step_v.argtypes = [C.POINTER(Model), C.POINTER(FwdArgs), P]
     L.nmarl_dial_msg.argtypes = [C.POINTER(Model), I, P, P, P, P]
+    L.nmarl_pack_weights.argtypes = [C.POINTER(Model), P, P, P, P]
     L.nmarl_rng_advance.argtypes = [P, U64, P]
     L.nmarl_nstep_return_adv.argtypes = [I, I, I, I, P, P, P, P, I, D, D, D, D, P, P, I, P, P, P]
     L.nmarl_loss_tiles.argtypes = [C.POINTER(Model), I]

@@ -11,6 +11,7 @@ the on-policy buffer (agents/utils.py:722-912), for B parallel environments:
                                  then states_bw := states_fw (policies.py:211)
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -22,7 +23,7 @@ NH = L.NH
 
 class PolicyEngine:
     def __init__(self, layout, n_env, n_step, hp, flat_params=None, device=None, rng_seed=0,
-                 distance_mask=None, coop_gamma=-1.0, group=None):
+                 distance_mask=None, coop_gamma=-1.0, group=None, use_tc=None):
         """hp: dict(v_coef, e_coef, max_grad_norm, alpha, epsilon, gamma, reward_norm, reward_clip)."""
         L.require_cuda()
         self.layout, self.B, self.T, self.hp = layout, int(n_env), int(n_step), dict(hp)
@@ -42,6 +43,12 @@ class PolicyEngine:
         self.grads = torch.zeros(layout.n_param, **f32)
         self.ms = torch.ones(layout.n_param, **f32)             # TF RMSProp slot starts at 1
         self.wt = torch.zeros(layout.n_wt, **f32)
+        # tcgen05 path: packed 3xTF32 operands; used by the kernels when B % 128 == 0
+        if use_tc is None:
+            use_tc = os.environ.get('NMARL_NO_TC', '0') != '1'
+        self.use_tc = bool(use_tc) and (self.B % 128 == 0)
+        self.wpack = torch.zeros(layout.n_wp, **f32) if self.use_tc else None
+        self.tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.c = [torch.zeros(N, B, NH, **f32) for _ in range(2)]
         self.h = [torch.zeros(N, B, NH, **f32) for _ in range(2)]
         self.msg = [torch.zeros(N, B, NH, **f32) for _ in range(2)] if self.variant == 'ma2c_dial' else [None, None]
@@ -78,6 +85,7 @@ class PolicyEngine:
         self._train_ready = False
         self.T_cur = T
         self.launches = 0
+        self.repack()
 
     # ---- state ----------------------------------------------------------------------------------
     def reset_states(self, mask=None):
@@ -90,6 +98,19 @@ class PolicyEngine:
             for t in (self.c[self.cur], self.h[self.cur], self.c_bw, self.h_bw):
                 t.mul_(keep)
         self._refresh_msg()
+
+    def repack(self):
+        """Refresh the packed tensor-core operands after any parameter change."""
+        if self.use_tc:
+            L.check(L.lib().nmarl_pack_weights(C.byref(self.model), L.ptr(self.params), L.ptr(self.wt), L.ptr(self.wpack),
+                                               L.stream()), 'nmarl_pack_weights')
+            self.launches += 8 * self.N
+
+    def check_tc(self):
+        """Host sync: raise if the tensor-core pipeline watchdog fired."""
+        code = int(self.tc_err.item())
+        if code:
+            raise RuntimeError('tcgen05 pipeline watchdog fired (code %d)' % code)
 
     def _refresh_msg(self):
         if self.variant == 'ma2c_dial':
@@ -122,6 +143,7 @@ class PolicyEngine:
         a.B = self.B
         a.params, a.obs, a.fp, a.done = L.ptr(self.params), L.ptr(obs), L.ptr(fp), L.ptr(done)
         a.c_in, a.h_in, a.msg_in = L.ptr(self.c[self.cur]), L.ptr(self.h[self.cur]), L.ptr(self.msg[self.cur])
+        a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
         return a
 
     def step_p(self, obs, fp, done, pi_out, action_out=None, sample_mode=L.SAMPLE_NONE, uniforms=None, rng_offset=0):
@@ -229,6 +251,7 @@ class PolicyEngine:
         a.dh_rec, a.dc_rec, a.dmsg = L.ptr(self.dh_rec), L.ptr(self.dc_rec), L.ptr(self.dmsg)
         a.wt, a.ws, a.ws_floats = L.ptr(self.wt), L.ptr(self.ws), self.ws_floats
         a.loss_part, a.grads = L.ptr(self.loss_part), L.ptr(self.grads)
+        a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
         return a
 
     def backward(self):
@@ -259,6 +282,7 @@ class PolicyEngine:
                                                 L.stream()), 'nmarl_clip_rmsprop_step')
         self.launches += 2
         self.c_bw.copy_(self.c[self.cur]); self.h_bw.copy_(self.h[self.cur])
+        self.repack()
         self._refresh_msg()        # DIAL: cached sender-side messages depend on the updated w_mfc
 
     def update(self, lr):

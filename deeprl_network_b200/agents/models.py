@@ -187,6 +187,7 @@ class IA2C:
         if save_file is not None and os.path.exists(model_dir + save_file + '.pt'):
             ck = torch.load(model_dir + save_file + '.pt', map_location='cpu')
             self.engine.params.copy_(ck['params']); self.engine.ms.copy_(ck['ms'])
+            self.engine.repack(); self.engine._refresh_msg()
             logging.info('Checkpoint loaded: %s' % save_file)
             return True
         logging.error('Can not find old checkpoint for %s' % model_dir)
@@ -198,6 +199,7 @@ class IA2C:
 
     def set_weights(self, params):
         self.engine.params.copy_(torch.from_numpy(self.layout.pack(params)))
+        self.engine.repack()
         self.engine._refresh_msg()
 
     # ---- batched entry points (n_env >= 1, device resident) ----------------------------------------------

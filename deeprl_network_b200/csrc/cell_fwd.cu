@@ -11,20 +11,9 @@
 //   lstm_comm  agents/utils.py:163-217      lstm_ic3  :378-417      lstm_dial :555-599
 //   lstm (IA2C) :87-115 + fc policies.py:145   heads policies.py:50-77   sampling utils.py:135-141
 //   A2C loss terms policies.py:236-255 (TRAIN mode: per-row loss + d/dlogits, d/dv)
-#include "common.cuh"
+#include "cell_common.cuh"
 
 namespace {
-
-enum { MODE_P = 0, MODE_V = 1, MODE_TRAIN = 2 };
-
-struct FwdK {
-  nmarl_fwd_args a;
-  // TRAIN-mode extras (all for one time step; pointers already offset to step t)
-  const float* Rs; const float* Advs;   // [N][B]
-  float* sv_xin; float* sv_sh; float* sv_gates; float* sv_enc; float* sv_dlv;
-  float* loss_part;                      // [N][tiles][4]
-  float loss_scale, v_coef, e_coef;
-};
 
 template <int BM, int KC>
 __host__ __device__ inline size_t fwd_region0_floats(const nmarl_model& m) {
@@ -348,7 +337,7 @@ __global__ void __launch_bounds__(16 * TY) cell_fwd_kernel(const __grid_constant
     if (tid < 3) {
       float s = 0.f;
       for (int w = 0; w < NT / 32; ++w) s += red[tid][w];
-      k.loss_part[((size_t)i * gridDim.x + blockIdx.x) * 4 + tid] = s;
+      k.loss_part[((size_t)i * k.loss_tiles + blockIdx.x) * 4 + tid] = s;
     }
   }
   if (VAR == NMARL_DIAL && MODE != MODE_V) {                            // sender-side message of the NEW h (utils.py:563-566)
@@ -425,6 +414,7 @@ int launch_fwd(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
 
 template <int MODE>
 int dispatch_fwd(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
+  if (nmarl_tc_fwd_supported(m, &k.a)) return nmarl_tc_launch_fwd(m, k, MODE, st);
   switch (m->variant) {
     case NMARL_IA2C: return launch_fwd<NMARL_IA2C, MODE>(m, k, st);
     case NMARL_NC: return launch_fwd<NMARL_NC, MODE>(m, k, st);
@@ -457,7 +447,9 @@ int check_model(const nmarl_model* m) {
 }  // namespace
 
 int nmarl_check_model(const nmarl_model* m) { return check_model(m); }
+int nmarl_fwd_tiles(int B) { return (B + 64 - 1) / 64; }
 
+int nmarl_fwd_tiles(int B);
 // entry used by train.cu for the TRAIN-mode forward of one time step
 int nmarl_launch_train_fwd(const nmarl_model* m, const nmarl_fwd_args* a, const float* Rs, const float* Advs,
                            float* sv_xin, float* sv_sh, float* sv_gates, float* sv_enc, float* sv_dlv,
@@ -466,11 +458,11 @@ int nmarl_launch_train_fwd(const nmarl_model* m, const nmarl_fwd_args* a, const 
   k.a = *a;
   k.Rs = Rs; k.Advs = Advs;
   k.sv_xin = sv_xin; k.sv_sh = sv_sh; k.sv_gates = sv_gates; k.sv_enc = sv_enc; k.sv_dlv = sv_dlv;
-  k.loss_part = loss_part; k.loss_scale = loss_scale; k.v_coef = v_coef; k.e_coef = e_coef;
+  k.loss_part = loss_part; k.loss_tiles = nmarl_fwd_tiles(a->B); k.loss_scale = loss_scale; k.v_coef = v_coef; k.e_coef = e_coef;
   return dispatch_fwd<MODE_TRAIN>(m, k, st);
 }
 
-int nmarl_fwd_tiles(int B) { return (B + FWD_BM - 1) / FWD_BM; }
+
 
 extern "C" int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a, void* stream) {
   if (check_model(m)) return 1;

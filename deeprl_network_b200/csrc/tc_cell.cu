@@ -1,0 +1,634 @@
+// tc_cell.cu -- tcgen05 (5th-gen tensor core) version of the fused forward cell (K2..K6):
+// every GEMM of the step (obs / fingerprint / message encoders and the LSTM gate GEMM) runs as
+// 3xTF32 tcgen05.mma with FP32 accumulators in TMEM; CUDA cores only do the elementwise epilogues.
+//
+// One CTA = 128 envs of one agent (UMMA M = 128).  192 threads:
+//   warps 0-3  "row threads": thread r owns env row r (TMEM lane r).  They gather the row's inputs,
+//              split them hi/lo and tcgen05.st them as the A operand (A lives in TMEM, so no shared
+//              memory is spent on activations), read encoder results back with tcgen05.ld, apply
+//              bias/activation, feed them to the gate GEMM, and finally run the LSTM cell update,
+//              the heads, softmax and sampling for their row.
+//   warp 4     B producer: one cp.async.bulk (TMA engine) per 32-wide k-block of pre-packed,
+//              128B-swizzled [hi | lo] weight tiles into a 3-stage shared-memory ring (mbarrier tx).
+//   warp 5     MMA issuer: a single elected thread issues tcgen05.mma kind::tf32 (3 per k-step:
+//              hi*hi + hi*lo + lo*hi) and tcgen05.commit's completion onto the ring barriers.
+// TMEM (512 columns): [0,256) gate accumulator, [256,320) encoder accumulator, [320,448) A-operand
+// ring (2 slots x (hi 32 | lo 32)).
+//
+// Same math, same argument block and same outputs as cell_fwd.cu (FP32 FFMA); used when
+// B % 128 == 0 and packed weights are supplied.  Restates the same reference lines as cell_fwd.cu.
+#include "cell_common.cuh"
+#include "tc.cuh"
+
+int nmarl_launch_pack_b(const float* W, int ldw, int K, int n0, int nrows, float* out, cudaStream_t st);
+
+namespace {
+
+constexpr int S_STAGES = 3;
+constexpr uint32_t STAGE_BYTES = 2 * 256 * 128;          // hi+lo tiles of the widest operand (N = 256)
+constexpr uint32_t ACC_COL = 0, ENC_COL = 256, A_COL = 320;
+constexpr int MAX_KB = 40;
+
+struct KbEnt {
+  uint32_t off_bytes, bytes;
+  uint8_t ksteps, n64, first, last_enc, last_acc, pad0, pad1, pad2;
+};
+
+struct RowCtx {
+  uint32_t tmem, lane_base;
+  uint64_t* a_full; uint64_t* a_empty; uint64_t* enc_full;
+  int q, e;
+  int* err;
+};
+
+__device__ __forceinline__ void produce_begin(RowCtx& c) {
+  const int slot = c.q & 1;
+  tc::mbar_wait(&c.a_empty[slot], ((c.q >> 1) & 1) ^ 1, c.err, 11);
+  tc::fence_after_sync();
+}
+__device__ __forceinline__ void produce_16(RowCtx& c, int half, const float (&x)[16]) {
+  const uint32_t col = A_COL + (c.q & 1) * 64 + half * 16;
+  tc::tmem_st_hilo16(c.tmem + c.lane_base + col, c.tmem + c.lane_base + col + 32, x);
+}
+__device__ __forceinline__ void produce_end(RowCtx& c) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  tc::mbar_arrive(&c.a_full[c.q & 1]);
+  c.q++;
+}
+// produce one 32-wide k-block from 32 registers
+__device__ __forceinline__ void produce_32(RowCtx& c, const float (&x)[32]) {
+  produce_begin(c);
+  float t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = x[j];
+  produce_16(c, 0, t);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = x[16 + j];
+  produce_16(c, 1, t);
+  produce_end(c);
+}
+// encoder accumulator (64 columns) -> registers
+__device__ __forceinline__ void enc_load(RowCtx& c, float (&v)[64]) {
+  tc::mbar_wait(c.enc_full, c.e & 1, c.err, 12);
+  c.e++;
+  tc::fence_after_sync();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t[16];
+    tc::tmem_ld16(c.tmem + c.lane_base + ENC_COL + 16 * q, t);
+    tc::wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[16 * q + j] = t[j];
+  }
+  tc::fence_before_sync();
+}
+// two gate k-blocks from 64 activations
+__device__ __forceinline__ void produce_64(RowCtx& c, const float (&s)[64]) {
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    produce_begin(c);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) t[j] = s[hb * 32 + half * 16 + j];
+      produce_16(c, half, t);
+    }
+    produce_end(c);
+  }
+}
+__device__ __forceinline__ void store64(float* dst, const float (&s)[64]) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+}
+__device__ __forceinline__ void bias_act64(float (&v)[64], const float* __restrict__ b, int act /*0 relu 1 tanh 2 none*/) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + q);
+    const float z[4] = {v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[4 * q + j] = act == 0 ? fmaxf(z[j], 0.f) : (act == 1 ? tanhf(z[j]) : z[j]);
+  }
+}
+
+template <int VAR, int MODE>
+__global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_constant__ nmarl_model m,
+                                                             const __grid_constant__ FwdK k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bst = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
+  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
+  uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
+  KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
+  __shared__ float red[3][4];
+
+  const nmarl_fwd_args& a = k.a;
+  const int i = blockIdx.y;
+  const nmarl_agent& ag = m.agent[i];
+  const int B = a.B, b0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_a = m.n_a, SD = m.s_dim;
+  const float* __restrict__ P = a.params;
+  const int Kx = ag.x_nsrc * ag.x_w;
+
+  if (tid == 0) {
+    for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], 128); tc::mbar_init(&a_empty[s], 1); }
+    tc::mbar_init(enc_full, 1);
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+    // ---- k-block schedule shared by the three roles --------------------------------------------------
+    int n = 0;
+    auto add = [&](int off_floats, int N, int K, int kb, int first, int last_enc, int last_acc) {
+      KbEnt e;
+      e.off_bytes = (uint32_t)(off_floats + kb * 2 * N * 32) * 4u;
+      e.bytes = 2u * N * 128u;
+      const int k8 = (K + 7) / 8 * 8;
+      e.ksteps = (uint8_t)min(4, (k8 - kb * 32) / 8);
+      e.n64 = (N == 64); e.first = first; e.last_enc = last_enc; e.last_acc = last_acc;
+      e.pad0 = e.pad1 = e.pad2 = 0;
+      sched[n++] = e;
+    };
+    const int KG = SD + NH;                                    // gate GEMM depth
+    const int nG = KG / 32;
+    int g = 0;
+    auto gate2 = [&]() { for (int j = 0; j < 2; ++j, ++g) add(ag.tp_g, 256, KG, g, g == 0, 0, g == nG - 1); };
+    add(ag.tp_x, 64, Kx, 0, 1, 1, 0);                          // X (Kx <= 32 on this path)
+    if (VAR == NMARL_NC) {
+      gate2();
+      add(ag.tp_p, 64, ag.n_nbr * n_a, 0, 1, 1, 0);
+      gate2();
+      const int nM = 2 * ag.n_nbr;
+      for (int j = 0; j < nM; ++j) add(ag.tp_m, 64, NH * ag.n_nbr, j, j == 0, j == nM - 1, 0);
+      gate2();
+      gate2();
+    } else if (VAR == NMARL_IA2C) {
+      gate2();
+      gate2();
+    } else if (VAR == NMARL_IC3) {
+      for (int j = 0; j < 2; ++j) add(ag.tp_m, 64, NH, j, j == 0, j == 1, 0);
+      gate2();
+      gate2();
+    } else {
+      const int nM = 2 * ag.n_nbr;
+      for (int j = 0; j < nM; ++j) add(ag.tp_m, 64, NH * ag.n_nbr, j, j == 0, j == nM - 1, 0);
+      gate2();
+      gate2();
+      if (MODE != MODE_V)
+        for (int j = 0; j < 2; ++j) add(ag.tp_mfc, 64, NH, j, j == 0, j == 1, 0);
+    }
+    *n_kb_s = n;
+  }
+  if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_kb = *n_kb_s;
+  float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+
+  if (warp < 4) {
+    // =================================== row threads ===================================================
+    RowCtx c;
+    c.tmem = tmem; c.lane_base = (uint32_t)(warp * 32) << 16;
+    c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.err = a.tc_err;
+    const int b = b0 + tid;
+    const size_t row = (size_t)i * B + b;
+    const float nd = 1.0f - a.done[b];
+    const int LDI = m.kx_pad + m.kp_pad + m.km_pad;
+    float* xin_row = (MODE == MODE_TRAIN) ? k.sv_xin + row * LDI : nullptr;
+    float* sh_row = (MODE == MODE_TRAIN) ? k.sv_sh + row * (SD + NH) : nullptr;
+
+    // ---- X encoder input: own + neighbours' observation rows --------------------------------------------
+    {
+      float xv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) xv[j] = 0.f;
+      for (int s = 0; s < ag.x_nsrc; ++s) {
+        const float* o = a.obs + ((size_t)ag.x_src[s] * B + b) * m.obs_stride;
+        for (int f = 0; f < ag.x_w; ++f) {
+          const float val = o[f];
+          const int kk = s * ag.x_w + f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j == kk) xv[j] = val;
+        }
+      }
+      if (MODE == MODE_TRAIN)
+        for (int q = 0; q < m.kx_pad / 4; ++q)
+          *reinterpret_cast<float4*>(xin_row + 4 * q) = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
+      produce_32(c, xv);
+    }
+    float s0[64];                       // encoder output being assembled
+    enc_load(c, s0);
+    bias_act64(s0, P + ag.o_b_ob, VAR == NMARL_IC3 ? 1 : 0);
+    if (MODE == MODE_TRAIN && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store64(k.sv_enc + row * 128, s0);
+
+    if (VAR == NMARL_NC) {
+      if (MODE == MODE_TRAIN) store64(sh_row, s0);
+      produce_64(c, s0);
+      // ---- fingerprint encoder ----
+      {
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = 0.f;
+        for (int s = 0; s < ag.n_nbr; ++s) {
+          const float* o = a.fp + ((size_t)ag.nbr[s] * B + b) * n_a;
+          for (int f = 0; f < n_a; ++f) {
+            const float val = o[f];
+            const int kk = s * n_a + f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j == kk) pv[j] = val;
+          }
+        }
+        if (MODE == MODE_TRAIN)
+          for (int q = 0; q < m.kp_pad / 4; ++q)
+            *reinterpret_cast<float4*>(xin_row + m.kx_pad + 4 * q) = make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
+        produce_32(c, pv);
+      }
+      enc_load(c, s0);
+      bias_act64(s0, P + ag.o_b_fp, 0);
+      if (MODE == MODE_TRAIN) store64(sh_row + NH, s0);
+      produce_64(c, s0);
+    }
+    if (VAR != NMARL_IA2C) {
+      // ---- message encoder: neighbours' UN-masked h (NC), their mean (IC3) or their messages (DIAL) ----
+      float* xm = (MODE == MODE_TRAIN) ? xin_row + m.kx_pad + m.kp_pad : nullptr;
+      if (VAR == NMARL_IC3) {
+        const float nn = (float)ag.n_nbr;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          float mv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mv[j] = 0.f;
+          for (int s = 0; s < ag.n_nbr; ++s) {
+            const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
+              mv[4 * q] += w.x; mv[4 * q + 1] += w.y; mv[4 * q + 2] += w.z; mv[4 * q + 3] += w.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mv[j] /= nn;
+          if (MODE == MODE_TRAIN)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(xm + hb * 32 + 4 * q) = make_float4(mv[4 * q], mv[4 * q + 1], mv[4 * q + 2], mv[4 * q + 3]);
+          produce_32(c, mv);
+        }
+      } else {
+        const float* src = (VAR == NMARL_NC) ? a.h_in : a.msg_in;
+        for (int s = 0; s < ag.n_nbr; ++s) {
+          const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            float mv[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 w = *reinterpret_cast<const float4*>(hp + hb * 32 + 4 * q);
+              mv[4 * q] = w.x; mv[4 * q + 1] = w.y; mv[4 * q + 2] = w.z; mv[4 * q + 3] = w.w;
+              if (MODE == MODE_TRAIN) *reinterpret_cast<float4*>(xm + s * NH + hb * 32 + 4 * q) = w;
+            }
+            produce_32(c, mv);
+          }
+        }
+        if (MODE == MODE_TRAIN)
+          for (int q = ag.n_nbr * 16; q < m.km_pad / 4; ++q) *reinterpret_cast<float4*>(xm + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float s1[64];
+      enc_load(c, s1);
+      if (VAR == NMARL_NC) {
+        bias_act64(s1, P + ag.o_b_msg, 0);
+        if (MODE == MODE_TRAIN) store64(sh_row + 2 * NH, s1);
+        produce_64(c, s1);
+      } else if (VAR == NMARL_IC3) {
+        bias_act64(s1, P + ag.o_b_msg, 2);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s0[j] += s1[j];
+        if (MODE == MODE_TRAIN) store64(sh_row, s0);
+        produce_64(c, s0);
+      } else {  // DIAL
+        bias_act64(s1, P + ag.o_b_msg, 0);
+        if (MODE == MODE_TRAIN) store64(k.sv_enc + row * 128 + NH, s1);
+        int am = 0;
+        {
+          const float* pr = a.fp + row * n_a;
+          float best = pr[0];
+          for (int cc = 1; cc < n_a; ++cc) { const float pv = pr[cc]; if (pv > best) { best = pv; am = cc; } }
+        }
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s0[j] = (s0[j] + s1[j]) + (j == am ? 1.0f : 0.0f);
+        if (MODE == MODE_TRAIN) store64(sh_row, s0);
+        produce_64(c, s0);
+      }
+    } else {
+      if (MODE == MODE_TRAIN) store64(sh_row, s0);
+      produce_64(c, s0);
+    }
+    // ---- own h (done-masked) ------------------------------------------------------------------------------
+    {
+      float hv[64];
+      const float* hp = a.h_in + row * NH;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
+        hv[4 * q] = w.x * nd; hv[4 * q + 1] = w.y * nd; hv[4 * q + 2] = w.z * nd; hv[4 * q + 3] = w.w * nd;
+      }
+      if (MODE == MODE_TRAIN) store64(sh_row + SD, hv);
+      produce_64(c, hv);
+    }
+
+    // ---- LSTM cell update + heads, 16 hidden units at a time ------------------------------------------------
+    tc::mbar_wait(acc_full, 0, a.tc_err, 13);
+    tc::fence_after_sync();
+    float logit[NMARL_MAX_NA];
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
+    float v = 0.f;
+#pragma unroll 1
+    for (int u0 = 0; u0 < NH; u0 += 16) {
+      float gi[16], gf[16], go[16], gu[16];
+      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 0 * NH + u0, gi);
+      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 1 * NH + u0, gf);
+      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 2 * NH + u0, go);
+      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 3 * NH + u0, gu);
+      tc::wait_ld();
+      float cn[16], hn[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 cp4 = *reinterpret_cast<const float4*>(a.c_in + row * NH + u0 + 4 * q);
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 0 * NH + u0) + q);
+        const float4 bf = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 1 * NH + u0) + q);
+        const float4 bo = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 2 * NH + u0) + q);
+        const float4 bu = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 3 * NH + u0) + q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = 4 * q + j;
+          gi[x] = sigmoidf_(gi[x] + f4get(bi, j));
+          gf[x] = sigmoidf_(gf[x] + f4get(bf, j));
+          go[x] = sigmoidf_(go[x] + f4get(bo, j));
+          gu[x] = tanhf(gu[x] + f4get(bu, j));
+          cn[x] = gf[x] * (f4get(cp4, j) * nd) + gi[x] * gu[x];
+          hn[x] = go[x] * tanhf(cn[x]);
+        }
+      }
+      if (MODE != MODE_V) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(a.c_out + row * NH + u0 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+          *reinterpret_cast<float4*>(a.h_out + row * NH + u0 + 4 * q) = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+        }
+      }
+      if (MODE == MODE_TRAIN) {
+        float* gs = k.sv_gates + row * NG + u0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(gs + 0 * NH + 4 * q) = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
+          *reinterpret_cast<float4*>(gs + 1 * NH + 4 * q) = make_float4(gf[4 * q], gf[4 * q + 1], gf[4 * q + 2], gf[4 * q + 3]);
+          *reinterpret_cast<float4*>(gs + 2 * NH + 4 * q) = make_float4(go[4 * q], go[4 * q + 1], go[4 * q + 2], go[4 * q + 3]);
+          *reinterpret_cast<float4*>(gs + 3 * NH + 4 * q) = make_float4(gu[4 * q], gu[4 * q + 1], gu[4 * q + 2], gu[4 * q + 3]);
+        }
+      }
+      if (MODE != MODE_V) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x)
+#pragma unroll
+          for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+            if (cc < n_a) logit[cc] = fmaf(hn[x], __ldg(P + ag.o_pi_w + (u0 + x) * n_a + cc), logit[cc]);
+      }
+      if (MODE != MODE_P) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) v = fmaf(hn[x], __ldg(P + ag.o_v_w + u0 + x), v);
+      }
+      if (VAR == NMARL_DIAL && MODE != MODE_V) {          // feed h' to the sender-side message fc
+        if ((u0 & 31) == 0) produce_begin(c);
+        produce_16(c, (u0 >> 4) & 1, hn);
+        if ((u0 & 31) == 16) produce_end(c);
+      }
+    }
+    tc::fence_before_sync();
+
+    // ---- heads (thread == env row), identical to cell_fwd.cu -----------------------------------------------
+    float pi[NMARL_MAX_NA];
+    if (MODE != MODE_V) {
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+        if (cc < n_a) { logit[cc] += __ldg(P + ag.o_pi_b + cc); mx = fmaxf(mx, logit[cc]); }
+      float se = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+        if (cc < n_a) { pi[cc] = expf(logit[cc] - mx); se += pi[cc]; } else pi[cc] = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+        if (cc < n_a) { pi[cc] = pi[cc] / se; if (a.pi != nullptr) a.pi[row * n_a + cc] = pi[cc]; }
+    }
+    if (MODE == MODE_P && a.action != nullptr && a.sample_mode != NMARL_SAMPLE_NONE) {
+      int act = 0;
+      if (a.sample_mode == NMARL_SAMPLE_GREEDY) {
+        float best = pi[0];
+#pragma unroll
+        for (int cc = 1; cc < NMARL_MAX_NA; ++cc) if (cc < n_a && pi[cc] > best) { best = pi[cc]; act = cc; }
+      } else {
+        double u;
+        if (a.sample_mode == NMARL_SAMPLE_UNIFORM) u = a.uniforms[row];
+        else u = philox_u01(a.rng[0], a.rng[1] + a.rng_offset, (uint32_t)row, 0x41435431u);
+        double cdf[NMARL_MAX_NA];
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc) { if (cc < n_a) s += (double)pi[cc]; cdf[cc] = s; }
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += ((cdf[cc] / s) <= u) ? 1 : 0;
+        act = min(act, n_a - 1);
+      }
+      a.action[row] = act;
+    }
+    if (MODE != MODE_P) {
+      for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + a.act_in[(size_t)ag.nbr[s] * B + b]);
+      v += __ldg(P + ag.o_v_b);
+      if (a.v != nullptr) a.v[row] = v;
+    }
+    if (MODE == MODE_TRAIN) {
+      const int act = a.act_in[row];
+      const float R = k.Rs[row], Adv = k.Advs[row];
+      const float cs = k.loss_scale;
+      float g[NMARL_MAX_NA];
+      float ent = 0.f, dot = 0.f, lpa = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < NMARL_MAX_NA; ++cc) {
+        g[cc] = 0.f;
+        if (cc < n_a) {
+          const float pc = fminf(fmaxf(pi[cc], 1e-10f), 1.0f);
+          const float in_rng = (pi[cc] >= 1e-10f && pi[cc] <= 1.0f) ? 1.0f : 0.0f;
+          const float lp = logf(pc);
+          ent -= pi[cc] * lp;
+          g[cc] = k.e_coef * cs * (lp + in_rng);
+          if (cc == act) { g[cc] += -cs * Adv * in_rng / pc; lpa = lp; }
+          dot += pi[cc] * g[cc];
+        }
+      }
+      float dl[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) dl[cc] = (cc < n_a) ? pi[cc] * (g[cc] - dot) : 0.f;
+      const float dvv = -k.v_coef * cs * (R - v);
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dl[cc] = dvv;
+      *reinterpret_cast<float4*>(k.sv_dlv + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+      *reinterpret_cast<float4*>(k.sv_dlv + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+      l_pol = -lpa * Adv; l_val = (R - v) * (R - v); l_ent = ent;
+    }
+    if (VAR == NMARL_DIAL && MODE != MODE_V) {            // msg' = relu(h' W_mfc + b)   (utils.py:563-566)
+      float mo[64];
+      enc_load(c, mo);
+      bias_act64(mo, P + ag.o_mfc_b, 0);
+      store64(a.msg_out + row * NH, mo);
+    }
+    if (MODE == MODE_TRAIN) {
+      float vals[3] = {l_pol, l_val, l_ent};
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        float x = vals[cc];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[cc][warp] = x;
+      }
+    }
+  } else if (warp == 4) {
+    // =================================== B producer ======================================================
+    if (lane == 0) {
+      const uint8_t* wp = reinterpret_cast<const uint8_t*>(a.wpack);
+      for (int q = 0; q < n_kb; ++q) {
+        const int st = q % S_STAGES;
+        tc::mbar_wait(&b_empty[st], ((q / S_STAGES) & 1) ^ 1, a.tc_err, 21);
+        const KbEnt e = sched[q];
+        tc::mbar_arrive_expect_tx(&b_full[st], e.bytes);
+        tc::bulk_g2s(bst + st * STAGE_BYTES, wp + e.off_bytes, e.bytes, &b_full[st]);
+      }
+    }
+  } else {
+    // =================================== MMA issuer ======================================================
+    if (lane == 0) {
+      for (int q = 0; q < n_kb; ++q) {
+        const int st = q % S_STAGES, slot = q & 1;
+        const KbEnt e = sched[q];
+        tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, a.tc_err, 31);
+        tc::mbar_wait(&a_full[slot], (q >> 1) & 1, a.tc_err, 32);
+        tc::fence_after_sync();
+        const uint32_t tile = e.bytes / 2;
+        const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile);
+        const uint32_t idesc = e.n64 ? tc::idesc_tf32(128, 64) : tc::idesc_tf32(128, 256);
+        const uint32_t dcol = tmem + (e.n64 ? ENC_COL : ACC_COL);
+        for (int ks = 0; ks < e.ksteps; ++ks) {
+          const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
+          tc::mma_tf32_ts(dcol, a_hi, d_hi + 2 * ks, idesc, (e.first && ks == 0) ? 0u : 1u);
+          tc::mma_tf32_ts(dcol, a_hi, d_lo + 2 * ks, idesc, 1u);
+          tc::mma_tf32_ts(dcol, a_lo, d_hi + 2 * ks, idesc, 1u);
+        }
+        tc::mma_commit(&a_empty[slot]);
+        tc::mma_commit(&b_empty[st]);
+        if (e.last_enc) tc::mma_commit(enc_full);
+        if (e.last_acc) tc::mma_commit(acc_full);
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE == MODE_TRAIN && tid < 3) {
+    const float s = ((red[tid][0] + red[tid][1]) + red[tid][2]) + red[tid][3];
+    float* lp = k.loss_part + ((size_t)i * k.loss_tiles + 2 * blockIdx.x) * 4;
+    lp[tid] = s;
+    lp[4 + tid] = 0.f;                 // the second 64-row slot of this 128-row tile
+  }
+  if (warp == 5) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
+}
+
+constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 16 * 8 + 16 + MAX_KB * sizeof(KbEnt);
+
+template <int VAR, int MODE>
+int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
+  auto kern = tc_cell_fwd_kernel<VAR, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    NMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    configured = true;
+  }
+  dim3 grid(k.a.B / 128, m->n_agent);
+  kern<<<grid, 192, TC_SMEM, st>>>(*m, k);
+  NMARL_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int VAR>
+int launch_tc_mode(const nmarl_model* m, const FwdK& k, int mode, cudaStream_t st) {
+  switch (mode) {
+    case MODE_P: return launch_tc<VAR, MODE_P>(m, k, st);
+    case MODE_V: return launch_tc<VAR, MODE_V>(m, k, st);
+    default: return launch_tc<VAR, MODE_TRAIN>(m, k, st);
+  }
+}
+
+}  // namespace
+
+bool nmarl_tc_fwd_supported(const nmarl_model* m, const nmarl_fwd_args* a) {
+  if (a->wpack == nullptr || a->B % 128 != 0 || m->kx_pad > 32 || m->kp_pad > 32) return false;
+  for (int i = 0; i < m->n_agent; ++i)
+    if (m->agent[i].tp_g < 0 || m->agent[i].tp_x < 0) return false;
+  return true;
+}
+
+int nmarl_tc_launch_fwd(const nmarl_model* m, const FwdK& k, int mode, cudaStream_t st) {
+  switch (m->variant) {
+    case NMARL_IA2C: return launch_tc_mode<NMARL_IA2C>(m, k, mode, st);
+    case NMARL_NC: return launch_tc_mode<NMARL_NC>(m, k, mode, st);
+    case NMARL_IC3: return launch_tc_mode<NMARL_IC3>(m, k, mode, st);
+    case NMARL_DIAL: return launch_tc_mode<NMARL_DIAL>(m, k, mode, st);
+  }
+  nmarl_set_error("unknown variant %d", m->variant);
+  return 1;
+}
+
+namespace {
+__global__ void tc_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int r = r0 + y, cidx = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < rows && cidx < cols) ? src[(size_t)r * cols + cidx] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int cidx = c0 + y, r = r0 + threadIdx.x;
+    if (r < rows && cidx < cols) dst[(size_t)cidx * rows + r] = tile[threadIdx.x][y];
+  }
+}
+}  // namespace
+
+extern "C" int nmarl_pack_weights(const nmarl_model* m, const float* params, float* wt, float* wpack, void* stream) {
+  NMARL_CHECK(m && params && wt && wpack, "pack_weights: missing buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int SD = m->s_dim;
+  dim3 blk(32, 8);
+  for (int i = 0; i < m->n_agent; ++i) {
+    const nmarl_agent& ag = m->agent[i];
+    const int Kx = ag.x_nsrc * ag.x_w;
+    const int Km = (m->variant == NMARL_IC3) ? NH : ag.n_nbr * NH;
+    // transposed copies (also used by the FFMA backward)
+    tc_transpose_kernel<<<dim3(NG / 32, (SD + NH + 31) / 32), blk, 0, st>>>(params + ag.o_wxh, wt + ag.t_wxh, SD + NH, NG);
+    if (m->variant != NMARL_IA2C && Km > 0)
+      tc_transpose_kernel<<<dim3(2, (Km + 31) / 32), blk, 0, st>>>(params + ag.o_w_msg, wt + ag.t_w_msg, Km, NH);
+    if (m->variant == NMARL_DIAL) tc_transpose_kernel<<<dim3(2, 2), blk, 0, st>>>(params + ag.o_mfc_w, wt + ag.t_mfc, NH, NH);
+    // forward operands
+    if (nmarl_launch_pack_b(params + ag.o_w_ob, NH, Kx, 0, NH, wpack + ag.tp_x, st)) return 1;
+    if (m->variant == NMARL_NC && nmarl_launch_pack_b(params + ag.o_w_fp, NH, ag.n_nbr * m->n_a, 0, NH, wpack + ag.tp_p, st)) return 1;
+    if (m->variant != NMARL_IA2C && Km > 0 && nmarl_launch_pack_b(params + ag.o_w_msg, NH, Km, 0, NH, wpack + ag.tp_m, st)) return 1;
+    if (nmarl_launch_pack_b(params + ag.o_wxh, NG, SD + NH, 0, NG, wpack + ag.tp_g, st)) return 1;
+    if (m->variant == NMARL_DIAL && nmarl_launch_pack_b(params + ag.o_mfc_w, NH, NH, 0, NH, wpack + ag.tp_mfc, st)) return 1;
+    // backward operands (from the transposed copies)
+    if (nmarl_launch_pack_b(wt + ag.t_wxh, SD + NH, NG, 0, SD + NH, wpack + ag.tp_gT, st)) return 1;
+    if (m->variant != NMARL_IA2C && Km > 0 && nmarl_launch_pack_b(wt + ag.t_w_msg, Km, NH, 0, Km, wpack + ag.tp_mT, st)) return 1;
+    if (m->variant == NMARL_DIAL && nmarl_launch_pack_b(wt + ag.t_mfc, NH, NH, 0, NH, wpack + ag.tp_mfcT, st)) return 1;
+  }
+  return 0;
+}

@@ -729,6 +729,7 @@ extern "C" int nmarl_a2c_train_forward(const nmarl_model* m, const nmarl_bwd_arg
     f.c_out = a->c_seq + (size_t)(t + 1) * nb * NH; f.h_out = a->h_seq + (size_t)(t + 1) * nb * NH;
     if (m->variant == NMARL_DIAL) { f.msg_in = a->msg_seq + (size_t)t * nb * NH; f.msg_out = a->msg_seq + (size_t)(t + 1) * nb * NH; }
     f.act_in = a->act + (size_t)t * nb;
+    f.wpack = a->wpack; f.tc_err = a->tc_err;
     int rc = nmarl_launch_train_fwd(m, &f, a->Rs + (size_t)t * nb, a->Advs + (size_t)t * nb,
                                     a->sv_xin + (size_t)t * nb * LDI, a->sv_sh + (size_t)t * nb * (m->s_dim + NH),
                                     a->sv_gates + (size_t)t * nb * NG, a->sv_enc ? a->sv_enc + (size_t)t * nb * 128 : nullptr,

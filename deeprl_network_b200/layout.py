@@ -82,6 +82,7 @@ class ModelLayout:
         self.agents_off = []
         off = 0
         toff = 0
+        poff = 0
 
         def put(name, shape):
             nonlocal off
@@ -94,7 +95,8 @@ class ModelLayout:
             nm = len(self.nbr[i])
             a = dict(p_begin=off)
             for k in ('o_w_ob', 'o_b_ob', 'o_w_fp', 'o_b_fp', 'o_w_msg', 'o_b_msg', 'o_wxh', 'o_b',
-                      'o_mfc_w', 'o_mfc_b', 'o_pi_w', 'o_pi_b', 'o_v_w', 'o_v_b', 't_wxh', 't_w_msg', 't_mfc'):
+                      'o_mfc_w', 'o_mfc_b', 'o_pi_w', 'o_pi_b', 'o_v_w', 'o_v_b', 't_wxh', 't_w_msg', 't_mfc',
+                      'tp_x', 'tp_p', 'tp_m', 'tp_g', 'tp_mfc', 'tp_gT', 'tp_mT', 'tp_mfcT'):
                 a[k] = -1
             kx = self._kx(i)
             if v == 'ia2c':
@@ -124,8 +126,26 @@ class ModelLayout:
             a['o_v_w'] = put(hv + '/w', (NH + n_a * nm, 1)); a['o_v_b'] = put(hv + '/b', (1,))
             a['t_wxh'] = toff; toff += 4 * NH * (self.s_dim + NH)
             a['p_end'] = off
+            # packed tensor-core operands: ceil(K/32) k-blocks x [hi|lo] x (N rows x 32 floats)
+            def tp(K, N):
+                nonlocal poff
+                o = poff
+                poff += ((K + 31) // 32) * 2 * N * 32
+                return o
+            a['tp_x'] = tp(kx, NH)
+            if v == 'ma2c_nc':
+                a['tp_p'] = tp(n_a * nm, NH)
+            if v != 'ia2c':
+                km2 = NH if v == 'ma2c_ic3' else NH * nm
+                a['tp_m'] = tp(km2, NH)
+                a['tp_mT'] = tp(NH, km2)
+            a['tp_g'] = tp(self.s_dim + NH, 4 * NH)
+            a['tp_gT'] = tp(4 * NH, self.s_dim + NH)
+            if v == 'ma2c_dial':
+                a['tp_mfc'] = tp(NH, NH)
+                a['tp_mfcT'] = tp(NH, NH)
             self.agents_off.append(a)
-        self.n_param, self.n_wt = off, max(toff, 4)
+        self.n_param, self.n_wt, self.n_wp = off, max(toff, 4), max(poff, 4)
         self.kx_pad = _up4(max(self._kx(i) for i in range(N)))
         max_nbr = max(len(x) for x in self.nbr)
         self.kp_pad = _up4(n_a * max_nbr) if v == 'ma2c_nc' else 0
@@ -141,7 +161,7 @@ class ModelLayout:
         m = L.Model()
         m.variant, m.n_agent, m.n_a, m.s_dim = self.vid, self.N, self.n_a, self.s_dim
         m.obs_stride, m.kx_pad, m.kp_pad, m.km_pad = self.obs_stride, self.kx_pad, self.kp_pad, self.km_pad
-        m.n_param, m.n_wt = self.n_param, self.n_wt
+        m.n_param, m.n_wt, m.n_wp = self.n_param, self.n_wt, self.n_wp
         m.per_agent_norm = 1 if self.variant == 'ia2c' else 0
         recv = [[] for _ in range(self.N)]
         for k in range(self.N):

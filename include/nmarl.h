@@ -57,6 +57,9 @@ typedef struct {
   int32_t t_w_msg;                       /* [64][k_m]                                           */
   int32_t t_mfc;                         /* [64][64]                                            */
   int32_t p_begin, p_end;                /* this agent's contiguous parameter range             */
+  /* offsets into the packed tensor-core operand buffer (nmarl_pack_weights); -1 = absent:              */
+  int32_t tp_x, tp_p, tp_m, tp_g, tp_mfc; /* encoders (N=64 tiles), gate [wx;wh] (N=256 tiles), DIAL mfc  */
+  int32_t tp_gT, tp_mT, tp_mfcT;         /* backward: [wx;wh]^T (N=s_dim+64), w_msg^T (N=k_m), w_mfc^T     */
 } nmarl_agent;
 
 typedef struct {
@@ -66,7 +69,7 @@ typedef struct {
   int32_t kx_pad, kp_pad, km_pad;        /* padded (x4) widths of the x~ / p~ / m~ input segments */
   int32_t n_param, n_wt;                 /* flat buffer sizes (floats)                          */
   int32_t per_agent_norm;                /* 1: clip each agent's range separately (IA2C)        */
-  int32_t _pad;
+  int32_t n_wp;                          /* floats in the packed tensor-core operand buffer     */
   nmarl_agent agent[NMARL_MAX_AGENT];
 } nmarl_model;
 
@@ -131,10 +134,17 @@ typedef struct {
   uint64_t rng_offset;     /* added to the device counter (distinct per call inside a graph)   */
   const int32_t* act_in;   /* v-call / train: [N][B] same-step actions                         */
   float* v;                /* v-call: [N][B]                                                   */
+  const float* wpack;      /* packed 3xTF32 operands (nmarl_pack_weights) or NULL.  When set and  */
+                           /* B % 128 == 0 the tcgen05 tensor-core kernel is used, else FP32 FFMA */
+  int32_t* tc_err;         /* device int: tensor-core pipeline watchdog (0 = ok); may be NULL      */
 } nmarl_fwd_args;
 
 int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
 int nmarl_policy_step_v(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
+/* Pack the GEMM weights for the tcgen05 path: per 32-wide k-block a [hi | lo] pair of 128B-swizzled
+ * K-major tiles of W^T (hi = value truncated to TF32, lo = remainder).  Call after every parameter
+ * change.  wt (transposed weights scratch, n_wt floats) is also refreshed.                           */
+int nmarl_pack_weights(const nmarl_model* m, const float* params, float* wt, float* wpack, void* stream);
 /* DIAL only: msg[N][B][64] = relu(h W_mfc + b) (agents/utils.py:563-566); needed after a reset */
 int nmarl_dial_msg(const nmarl_model* m, int B, const float* params, const float* h, float* msg, void* stream);
 /* advance the device Philox counter by n (one tiny kernel; keeps graph replays fresh) */
@@ -184,6 +194,8 @@ typedef struct {
   float* wt; float* ws; int64_t ws_floats;
   float* loss_part;
   float* grads;
+  const float* wpack;        /* packed tensor-core operands or NULL (see nmarl_fwd_args)            */
+  int32_t* tc_err;
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */

@@ -24,7 +24,7 @@ def _inputs(B, N=8, seed=0):
 
 
 @pytest.mark.parametrize('variant', VARIANTS)
-@pytest.mark.parametrize('B', [1, 37, 130])
+@pytest.mark.parametrize('B', [1, 37, 130, 128, 256])       # 128/256 take the tcgen05 path
 def test_p_and_v_calls_match_oracle(variant, B):
     from deeprl_network_b200 import _lib as L
     eng, orc, lay, _ = make_pair(variant, B)
@@ -45,6 +45,7 @@ def test_p_and_v_calls_match_oracle(variant, B):
         pk = bn(pi_d)
         exp = np.array([[OracleTrainer.choice(pk[b, i], u[b, i]) for i in range(8)] for b in range(B)])
         np.testing.assert_array_equal(bn(act_d), exp)
+        eng.check_tc()
         acts = rs.randint(0, 4, size=(B, 8))
         v_d = torch.zeros(8, B, device='cuda')
         eng.step_v(obs_d, fp_d, done_d, nb(acts).int(), v_d)
