@@ -86,6 +86,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_hilo8(uint32_t taddr_hi, uint32_t taddr_lo, const float (&x)[8]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t b = __float_as_uint(x[i]) & 0xFFFFE000u;
+    hi[i] = b;
+    lo[i] = __float_as_uint(x[i] - __uint_as_float(b));
+  }
+  tmem_st8(taddr_hi, hi);
+  tmem_st8(taddr_lo, lo);
+}
+
 // hi/lo split of 16 fp32 values and store as two TF32 operand chunks (hi at col, lo at col + lo_off)
 __device__ __forceinline__ void tmem_st_hilo16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&x)[16]) {
   uint32_t hi[16], lo[16];

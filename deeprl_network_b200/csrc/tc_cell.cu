@@ -2,15 +2,16 @@
 // every GEMM of the step (obs / fingerprint / message encoders and the LSTM gate GEMM) runs as
 // 3xTF32 tcgen05.mma with FP32 accumulators in TMEM; CUDA cores only do the elementwise epilogues.
 //
-// One CTA = 128 envs of one agent (UMMA M = 128).  192 threads:
-//   warps 0-3  "row threads": thread r owns env row r (TMEM lane r).  They gather the row's inputs,
-//              split them hi/lo and tcgen05.st them as the A operand (A lives in TMEM, so no shared
-//              memory is spent on activations), read encoder results back with tcgen05.ld, apply
-//              bias/activation, feed them to the gate GEMM, and finally run the LSTM cell update,
-//              the heads, softmax and sampling for their row.
-//   warp 4     B producer: one cp.async.bulk (TMA engine) per 32-wide k-block of pre-packed,
+// One CTA = 128 envs of one agent (UMMA M = 128).  576 threads:
+//   warps 0-15 "row threads": 4 warp-sets x 4 warps; a thread of set s in TMEM-lane quarter w owns env
+//              row r = 32 w + lane (TMEM lane r) and the column slice s of it.  They gather the row's
+//              inputs, split them hi/lo and tcgen05.st them as the A operand (A lives in TMEM, so no
+//              shared memory is spent on activations), read encoder results back with tcgen05.ld, apply
+//              bias/activation, feed them to the gate GEMM, and finally run the LSTM cell update, the
+//              heads, softmax and sampling for their row.
+//   warp 16    B producer: one cp.async.bulk (TMA engine) per 32-wide k-block of pre-packed,
 //              128B-swizzled [hi | lo] weight tiles into a 3-stage shared-memory ring (mbarrier tx).
-//   warp 5     MMA issuer: a single elected thread issues tcgen05.mma kind::tf32 (3 per k-step:
+//   warp 17    MMA issuer: a single elected thread issues tcgen05.mma kind::tf32 (3 per k-step:
 //              hi*hi + hi*lo + lo*hi) and tcgen05.commit's completion onto the ring barriers.
 // TMEM (512 columns): [0,256) gate accumulator, [256,320) encoder accumulator, [320,448) A-operand
 // ring (2 slots x (hi 32 | lo 32)).
@@ -28,6 +29,14 @@ constexpr int S_STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 2 * 256 * 128;          // hi+lo tiles of the widest operand (N = 256)
 constexpr uint32_t ACC_COL = 0, ENC_COL = 256, A_COL = 320;
 constexpr int MAX_KB = 40;
+// NSET warp-sets share every env row: set s of row r works on columns [s*W, (s+1)*W) of each 32-wide input
+// k-block and on hidden units [s*EW, (s+1)*EW) of the encoders / LSTM cell.  4 sets = 16 row warps per SM
+// (4 per scheduler) so global-load, TMEM and barrier latencies overlap across warps.
+constexpr int NSET = 4;
+constexpr int W = 32 / NSET, EW = 64 / NSET;
+constexpr int ROW_THREADS = 128 * NSET;
+constexpr int TC_THREADS = ROW_THREADS + 64;
+static_assert(W % 8 == 0 && EW % 8 == 0, "8-column TMEM pieces");
 
 struct KbEnt {
   uint32_t off_bytes, bytes;
@@ -37,7 +46,7 @@ struct KbEnt {
 struct RowCtx {
   uint32_t tmem, lane_base;
   uint64_t* a_full; uint64_t* a_empty; uint64_t* enc_full;
-  int q, e;
+  int q, e, set;
   int* err;
 };
 
@@ -46,9 +55,9 @@ __device__ __forceinline__ void produce_begin(RowCtx& c) {
   tc::mbar_wait(&c.a_empty[slot], ((c.q >> 1) & 1) ^ 1, c.err, 11);
   tc::fence_after_sync();
 }
-__device__ __forceinline__ void produce_16(RowCtx& c, int half, const float (&x)[16]) {
-  const uint32_t col = A_COL + (c.q & 1) * 64 + half * 16;
-  tc::tmem_st_hilo16(c.tmem + c.lane_base + col, c.tmem + c.lane_base + col + 32, x);
+__device__ __forceinline__ void produce_piece(RowCtx& c, int col /*0..31, multiple of 8*/, const float (&x)[8]) {
+  const uint32_t t = c.tmem + c.lane_base + A_COL + (c.q & 1) * 64 + col;
+  tc::tmem_st_hilo8(t, t + 32, x);
 }
 __device__ __forceinline__ void produce_end(RowCtx& c) {
   tc::wait_st();
@@ -56,65 +65,70 @@ __device__ __forceinline__ void produce_end(RowCtx& c) {
   tc::mbar_arrive(&c.a_full[c.q & 1]);
   c.q++;
 }
-// produce one 32-wide k-block from 32 registers
-__device__ __forceinline__ void produce_32(RowCtx& c, const float (&x)[32]) {
+// one input k-block: this thread contributes columns [set*W, set*W + W)
+__device__ __forceinline__ void produce_in(RowCtx& c, const float (&x)[W]) {
   produce_begin(c);
-  float t[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) t[j] = x[j];
-  produce_16(c, 0, t);
+  for (int p = 0; p < W / 8; ++p) {
+    float t[8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) t[j] = x[16 + j];
-  produce_16(c, 1, t);
+    for (int j = 0; j < 8; ++j) t[j] = x[8 * p + j];
+    produce_piece(c, c.set * W + 8 * p, t);
+  }
   produce_end(c);
 }
-// encoder accumulator (64 columns) -> registers
-__device__ __forceinline__ void enc_load(RowCtx& c, float (&v)[64]) {
-  tc::mbar_wait(c.enc_full, c.e & 1, c.err, 12);
-  c.e++;
-  tc::fence_after_sync();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float t[16];
-    tc::tmem_ld16(c.tmem + c.lane_base + ENC_COL + 16 * q, t);
-    tc::wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[16 * q + j] = t[j];
-  }
-  tc::fence_before_sync();
-}
-// two gate k-blocks from 64 activations
-__device__ __forceinline__ void produce_64(RowCtx& c, const float (&s)[64]) {
+// two k-blocks fed by a 64-wide activation vector of which this thread holds [set*EW, set*EW + EW)
+__device__ __forceinline__ void produce_act(RowCtx& c, const float (&s)[EW]) {
 #pragma unroll
   for (int hb = 0; hb < 2; ++hb) {
     produce_begin(c);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float t[16];
+    for (int p = 0; p < EW / 8; ++p) {
+      const int col = c.set * EW + 8 * p;
+      if ((col >> 5) == hb) {
+        float t[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) t[j] = s[hb * 32 + half * 16 + j];
-      produce_16(c, half, t);
+        for (int j = 0; j < 8; ++j) t[j] = s[8 * p + j];
+        produce_piece(c, col & 31, t);
+      }
     }
     produce_end(c);
   }
 }
-__device__ __forceinline__ void store64(float* dst, const float (&s)[64]) {
+// this thread's EW columns of the encoder accumulator
+__device__ __forceinline__ void enc_load(RowCtx& c, float (&v)[EW]) {
+  tc::mbar_wait(c.enc_full, c.e & 1, c.err, 12);
+  c.e++;
+  tc::fence_after_sync();
 #pragma unroll
-  for (int q = 0; q < 16; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+  for (int p = 0; p < EW / 8; ++p) {
+    float t[8];
+    tc::tmem_ld8(c.tmem + c.lane_base + ENC_COL + c.set * EW + 8 * p, t);
+    tc::wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[8 * p + j] = t[j];
+  }
+  tc::fence_before_sync();
 }
-__device__ __forceinline__ void bias_act64(float (&v)[64], const float* __restrict__ b, int act /*0 relu 1 tanh 2 none*/) {
+template <int NV>
+__device__ __forceinline__ void store_vec(float* dst, const float (&s)[NV]) {
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 0; q < NV / 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+}
+__device__ __forceinline__ void bias_act(float (&v)[EW], const float* __restrict__ b, int act /*0 relu 1 tanh 2 none*/) {
+#pragma unroll
+  for (int q = 0; q < EW / 4; ++q) {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + q);
     const float z[4] = {v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[4 * q + j] = act == 0 ? fmaxf(z[j], 0.f) : (act == 1 ? tanhf(z[j]) : z[j]);
   }
 }
+__device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
 
 template <int VAR, int MODE>
-__global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_constant__ nmarl_model m,
-                                                             const __grid_constant__ FwdK k) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid_constant__ nmarl_model m,
+                                                                    const __grid_constant__ FwdK k) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
@@ -124,6 +138,7 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
   KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
+  float* hpart = reinterpret_cast<float*>(sched + MAX_KB);       // [NSET][128][8] head partial sums
   __shared__ float red[3][4];
 
   const nmarl_fwd_args& a = k.a;
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], 128); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
@@ -183,76 +198,73 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
     }
     *n_kb_s = n;
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int n_kb = *n_kb_s;
-  float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
 
-  if (warp < 4) {
+  if (warp < ROW_THREADS / 32) {
     // =================================== row threads ===================================================
     RowCtx c;
-    c.tmem = tmem; c.lane_base = (uint32_t)(warp * 32) << 16;
-    c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.err = a.tc_err;
-    const int b = b0 + tid;
+    const int set = warp >> 2, quarter = warp & 3, r = quarter * 32 + lane;
+    c.tmem = tmem; c.lane_base = (uint32_t)(quarter * 32) << 16;
+    c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.set = set; c.err = a.tc_err;
+    const int b = b0 + r;
     const size_t row = (size_t)i * B + b;
     const float nd = 1.0f - a.done[b];
     const int LDI = m.kx_pad + m.kp_pad + m.km_pad;
     float* xin_row = (MODE == MODE_TRAIN) ? k.sv_xin + row * LDI : nullptr;
     float* sh_row = (MODE == MODE_TRAIN) ? k.sv_sh + row * (SD + NH) : nullptr;
+    const int c0 = set * W;             // this thread's columns inside every 32-wide input k-block
+    const int e0 = set * EW;            // this thread's hidden units / encoder columns
 
     // ---- X encoder input: own + neighbours' observation rows --------------------------------------------
     {
-      float xv[32];
+      float xv[W];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) xv[j] = 0.f;
-      for (int s = 0; s < ag.x_nsrc; ++s) {
-        const float* o = a.obs + ((size_t)ag.x_src[s] * B + b) * m.obs_stride;
-        for (int f = 0; f < ag.x_w; ++f) {
-          const float val = o[f];
-          const int kk = s * ag.x_w + f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j == kk) xv[j] = val;
+      for (int j = 0; j < W; ++j) {
+        const int kk = c0 + j;
+        float val = 0.f;
+        if (kk < Kx) {
+          const int s = kk / ag.x_w, f = kk - s * ag.x_w;
+          val = a.obs[((size_t)ag.x_src[s] * B + b) * m.obs_stride + f];
         }
+        xv[j] = val;
       }
-      if (MODE == MODE_TRAIN)
-        for (int q = 0; q < m.kx_pad / 4; ++q)
-          *reinterpret_cast<float4*>(xin_row + 4 * q) = make_float4(xv[4 * q], xv[4 * q + 1], xv[4 * q + 2], xv[4 * q + 3]);
-      produce_32(c, xv);
+      if (MODE == MODE_TRAIN && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
+      produce_in(c, xv);
     }
-    float s0[64];                       // encoder output being assembled
+    float s0[EW];                       // this thread's slice of the encoder output being assembled
     enc_load(c, s0);
-    bias_act64(s0, P + ag.o_b_ob, VAR == NMARL_IC3 ? 1 : 0);
-    if (MODE == MODE_TRAIN && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store64(k.sv_enc + row * 128, s0);
+    bias_act(s0, P + ag.o_b_ob + e0, VAR == NMARL_IC3 ? 1 : 0);
+    if (MODE == MODE_TRAIN && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
 
     if (VAR == NMARL_NC) {
-      if (MODE == MODE_TRAIN) store64(sh_row, s0);
-      produce_64(c, s0);
+      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+      produce_act(c, s0);
       // ---- fingerprint encoder ----
       {
-        float pv[32];
+        float pv[W];
+        const int Kp = ag.n_nbr * n_a;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) pv[j] = 0.f;
-        for (int s = 0; s < ag.n_nbr; ++s) {
-          const float* o = a.fp + ((size_t)ag.nbr[s] * B + b) * n_a;
-          for (int f = 0; f < n_a; ++f) {
-            const float val = o[f];
-            const int kk = s * n_a + f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j == kk) pv[j] = val;
+        for (int j = 0; j < W; ++j) {
+          const int kk = c0 + j;
+          float val = 0.f;
+          if (kk < Kp) {
+            const int s = kk / n_a, f = kk - s * n_a;
+            val = a.fp[((size_t)ag.nbr[s] * B + b) * n_a + f];
           }
+          pv[j] = val;
         }
-        if (MODE == MODE_TRAIN)
-          for (int q = 0; q < m.kp_pad / 4; ++q)
-            *reinterpret_cast<float4*>(xin_row + m.kx_pad + 4 * q) = make_float4(pv[4 * q], pv[4 * q + 1], pv[4 * q + 2], pv[4 * q + 3]);
-        produce_32(c, pv);
+        if (MODE == MODE_TRAIN && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
+        produce_in(c, pv);
       }
       enc_load(c, s0);
-      bias_act64(s0, P + ag.o_b_fp, 0);
-      if (MODE == MODE_TRAIN) store64(sh_row + NH, s0);
-      produce_64(c, s0);
+      bias_act(s0, P + ag.o_b_fp + e0, 0);
+      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + NH + e0, s0);
+      produce_act(c, s0);
     }
     if (VAR != NMARL_IA2C) {
       // ---- message encoder: neighbours' UN-masked h (NC), their mean (IC3) or their messages (DIAL) ----
@@ -261,59 +273,60 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
         const float nn = (float)ag.n_nbr;
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
-          float mv[32];
+          float mv[W];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mv[j] = 0.f;
+          for (int j = 0; j < W; ++j) mv[j] = 0.f;
           for (int s = 0; s < ag.n_nbr; ++s) {
-            const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32;
+            const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < W / 4; ++q) {
               const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
               mv[4 * q] += w.x; mv[4 * q + 1] += w.y; mv[4 * q + 2] += w.z; mv[4 * q + 3] += w.w;
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mv[j] /= nn;
-          if (MODE == MODE_TRAIN)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(xm + hb * 32 + 4 * q) = make_float4(mv[4 * q], mv[4 * q + 1], mv[4 * q + 2], mv[4 * q + 3]);
-          produce_32(c, mv);
+          for (int j = 0; j < W; ++j) mv[j] /= nn;
+          if (MODE == MODE_TRAIN) store_vec<W>(xm + hb * 32 + c0, mv);
+          produce_in(c, mv);
         }
       } else {
         const float* src = (VAR == NMARL_NC) ? a.h_in : a.msg_in;
         for (int s = 0; s < ag.n_nbr; ++s) {
-          const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH;
+          const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH + c0;
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
-            float mv[32];
+            float mv[W];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < W / 4; ++q) {
               const float4 w = *reinterpret_cast<const float4*>(hp + hb * 32 + 4 * q);
               mv[4 * q] = w.x; mv[4 * q + 1] = w.y; mv[4 * q + 2] = w.z; mv[4 * q + 3] = w.w;
-              if (MODE == MODE_TRAIN) *reinterpret_cast<float4*>(xm + s * NH + hb * 32 + 4 * q) = w;
             }
-            produce_32(c, mv);
+            if (MODE == MODE_TRAIN) store_vec<W>(xm + s * NH + hb * 32 + c0, mv);
+            produce_in(c, mv);
           }
         }
-        if (MODE == MODE_TRAIN)
-          for (int q = ag.n_nbr * 16; q < m.km_pad / 4; ++q) *reinterpret_cast<float4*>(xm + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == MODE_TRAIN) {
+          float z[W];
+#pragma unroll
+          for (int j = 0; j < W; ++j) z[j] = 0.f;
+          for (int q = ag.n_nbr * 2; q < m.km_pad / 32; ++q) store_vec<W>(xm + q * 32 + c0, z);
+        }
       }
-      float s1[64];
+      float s1[EW];
       enc_load(c, s1);
       if (VAR == NMARL_NC) {
-        bias_act64(s1, P + ag.o_b_msg, 0);
-        if (MODE == MODE_TRAIN) store64(sh_row + 2 * NH, s1);
-        produce_64(c, s1);
+        bias_act(s1, P + ag.o_b_msg + e0, 0);
+        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + 2 * NH + e0, s1);
+        produce_act(c, s1);
       } else if (VAR == NMARL_IC3) {
-        bias_act64(s1, P + ag.o_b_msg, 2);
+        bias_act(s1, P + ag.o_b_msg + e0, 2);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s0[j] += s1[j];
-        if (MODE == MODE_TRAIN) store64(sh_row, s0);
-        produce_64(c, s0);
+        for (int j = 0; j < EW; ++j) s0[j] += s1[j];
+        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+        produce_act(c, s0);
       } else {  // DIAL
-        bias_act64(s1, P + ag.o_b_msg, 0);
-        if (MODE == MODE_TRAIN) store64(k.sv_enc + row * 128 + NH, s1);
+        bias_act(s1, P + ag.o_b_msg + e0, 0);
+        if (MODE == MODE_TRAIN) store_vec<EW>(k.sv_enc + row * 128 + NH + e0, s1);
         int am = 0;
         {
           const float* pr = a.fp + row * n_a;
@@ -321,28 +334,29 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
           for (int cc = 1; cc < n_a; ++cc) { const float pv = pr[cc]; if (pv > best) { best = pv; am = cc; } }
         }
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s0[j] = (s0[j] + s1[j]) + (j == am ? 1.0f : 0.0f);
-        if (MODE == MODE_TRAIN) store64(sh_row, s0);
-        produce_64(c, s0);
+        for (int j = 0; j < EW; ++j) s0[j] = (s0[j] + s1[j]) + ((e0 + j) == am ? 1.0f : 0.0f);
+        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+        produce_act(c, s0);
       }
     } else {
-      if (MODE == MODE_TRAIN) store64(sh_row, s0);
-      produce_64(c, s0);
+      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+      produce_act(c, s0);
     }
-    // ---- own h (done-masked) ------------------------------------------------------------------------------
-    {
-      float hv[64];
-      const float* hp = a.h_in + row * NH;
+    // ---- own h (done-masked): two input k-blocks --------------------------------------------------------------
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
+    for (int hb = 0; hb < 2; ++hb) {
+      float hv[W];
+      const float* hp = a.h_in + row * NH + hb * 32 + c0;
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q) {
         const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
         hv[4 * q] = w.x * nd; hv[4 * q + 1] = w.y * nd; hv[4 * q + 2] = w.z * nd; hv[4 * q + 3] = w.w * nd;
       }
-      if (MODE == MODE_TRAIN) store64(sh_row + SD, hv);
-      produce_64(c, hv);
+      if (MODE == MODE_TRAIN) store_vec<W>(sh_row + SD + hb * 32 + c0, hv);
+      produce_in(c, hv);
     }
 
-    // ---- LSTM cell update + heads, 16 hidden units at a time ------------------------------------------------
+    // ---- LSTM cell update for hidden units [e0, e0 + EW), 8 at a time; partial head sums -----------------------
     tc::mbar_wait(acc_full, 0, a.tc_err, 13);
     tc::fence_after_sync();
     float logit[NMARL_MAX_NA];
@@ -350,16 +364,16 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
     for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
     float v = 0.f;
 #pragma unroll 1
-    for (int u0 = 0; u0 < NH; u0 += 16) {
-      float gi[16], gf[16], go[16], gu[16];
-      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 0 * NH + u0, gi);
-      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 1 * NH + u0, gf);
-      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 2 * NH + u0, go);
-      tc::tmem_ld16(tmem + c.lane_base + ACC_COL + 3 * NH + u0, gu);
+    for (int u0 = e0; u0 < e0 + EW; u0 += 8) {
+      float gi[8], gf[8], go[8], gu[8];
+      tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 0 * NH + u0, gi);
+      tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 1 * NH + u0, gf);
+      tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 2 * NH + u0, go);
+      tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 3 * NH + u0, gu);
       tc::wait_ld();
-      float cn[16], hn[16];
+      float cn[8], hn[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         const float4 cp4 = *reinterpret_cast<const float4*>(a.c_in + row * NH + u0 + 4 * q);
         const float4 bi = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 0 * NH + u0) + q);
         const float4 bf = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 1 * NH + u0) + q);
@@ -377,126 +391,137 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
         }
       }
       if (MODE != MODE_V) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<float4*>(a.c_out + row * NH + u0 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
-          *reinterpret_cast<float4*>(a.h_out + row * NH + u0 + 4 * q) = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
-        }
+        store_vec<8>(a.c_out + row * NH + u0, cn);
+        store_vec<8>(a.h_out + row * NH + u0, hn);
       }
       if (MODE == MODE_TRAIN) {
         float* gs = k.sv_gates + row * NG + u0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<float4*>(gs + 0 * NH + 4 * q) = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
-          *reinterpret_cast<float4*>(gs + 1 * NH + 4 * q) = make_float4(gf[4 * q], gf[4 * q + 1], gf[4 * q + 2], gf[4 * q + 3]);
-          *reinterpret_cast<float4*>(gs + 2 * NH + 4 * q) = make_float4(go[4 * q], go[4 * q + 1], go[4 * q + 2], go[4 * q + 3]);
-          *reinterpret_cast<float4*>(gs + 3 * NH + 4 * q) = make_float4(gu[4 * q], gu[4 * q + 1], gu[4 * q + 2], gu[4 * q + 3]);
-        }
+        store_vec<8>(gs + 0 * NH, gi); store_vec<8>(gs + 1 * NH, gf); store_vec<8>(gs + 2 * NH, go); store_vec<8>(gs + 3 * NH, gu);
       }
       if (MODE != MODE_V) {
 #pragma unroll
-        for (int x = 0; x < 16; ++x)
+        for (int x = 0; x < 8; ++x)
 #pragma unroll
           for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
             if (cc < n_a) logit[cc] = fmaf(hn[x], __ldg(P + ag.o_pi_w + (u0 + x) * n_a + cc), logit[cc]);
       }
       if (MODE != MODE_P) {
 #pragma unroll
-        for (int x = 0; x < 16; ++x) v = fmaf(hn[x], __ldg(P + ag.o_v_w + u0 + x), v);
+        for (int x = 0; x < 8; ++x) v = fmaf(hn[x], __ldg(P + ag.o_v_w + u0 + x), v);
       }
-      if (VAR == NMARL_DIAL && MODE != MODE_V) {          // feed h' to the sender-side message fc
-        if ((u0 & 31) == 0) produce_begin(c);
-        produce_16(c, (u0 >> 4) & 1, hn);
-        if ((u0 & 31) == 16) produce_end(c);
+      if (VAR == NMARL_DIAL && MODE != MODE_V) {          // stash h' for the sender-side message fc below
+#pragma unroll
+        for (int x = 0; x < 8; ++x) s0[(u0 - e0) + x] = hn[x];
       }
     }
     tc::fence_before_sync();
+    if (VAR == NMARL_DIAL && MODE != MODE_V) produce_act(c, s0);
 
-    // ---- heads (thread == env row), identical to cell_fwd.cu -----------------------------------------------
-    float pi[NMARL_MAX_NA];
-    if (MODE != MODE_V) {
-      float mx = -3.0e38f;
+    // ---- heads: combine the NSET partial sums of a row in fixed order, then softmax / sampling / loss -------
+    {
+      float* hp = hpart + ((size_t)set * 128 + r) * 8;
 #pragma unroll
-      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
-        if (cc < n_a) { logit[cc] += __ldg(P + ag.o_pi_b + cc); mx = fmaxf(mx, logit[cc]); }
-      float se = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
-        if (cc < n_a) { pi[cc] = expf(logit[cc] - mx); se += pi[cc]; } else pi[cc] = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
-        if (cc < n_a) { pi[cc] = pi[cc] / se; if (a.pi != nullptr) a.pi[row * n_a + cc] = pi[cc]; }
+      for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc) hp[cc] = logit[cc];
+      hp[NMARL_MAX_NA - 1] = v;
     }
-    if (MODE == MODE_P && a.action != nullptr && a.sample_mode != NMARL_SAMPLE_NONE) {
-      int act = 0;
-      if (a.sample_mode == NMARL_SAMPLE_GREEDY) {
-        float best = pi[0];
+    row_barrier();
+    float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+    if (set == 0) {
 #pragma unroll
-        for (int cc = 1; cc < NMARL_MAX_NA; ++cc) if (cc < n_a && pi[cc] > best) { best = pi[cc]; act = cc; }
-      } else {
-        double u;
-        if (a.sample_mode == NMARL_SAMPLE_UNIFORM) u = a.uniforms[row];
-        else u = philox_u01(a.rng[0], a.rng[1] + a.rng_offset, (uint32_t)row, 0x41435431u);
-        double cdf[NMARL_MAX_NA];
-        double s = 0.0;
+      for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
+      v = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < NMARL_MAX_NA; ++cc) { if (cc < n_a) s += (double)pi[cc]; cdf[cc] = s; }
+      for (int s = 0; s < NSET; ++s) {
+        const float* hp = hpart + ((size_t)s * 128 + r) * 8;
 #pragma unroll
-        for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += ((cdf[cc] / s) <= u) ? 1 : 0;
-        act = min(act, n_a - 1);
+        for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc) logit[cc] += hp[cc];
+        v += hp[NMARL_MAX_NA - 1];
       }
-      a.action[row] = act;
-    }
-    if (MODE != MODE_P) {
-      for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + a.act_in[(size_t)ag.nbr[s] * B + b]);
-      v += __ldg(P + ag.o_v_b);
-      if (a.v != nullptr) a.v[row] = v;
-    }
-    if (MODE == MODE_TRAIN) {
-      const int act = a.act_in[row];
-      const float R = k.Rs[row], Adv = k.Advs[row];
-      const float cs = k.loss_scale;
-      float g[NMARL_MAX_NA];
-      float ent = 0.f, dot = 0.f, lpa = 0.f;
+      float pi[NMARL_MAX_NA];
+      if (MODE != MODE_V) {
+        float mx = -3.0e38f;
 #pragma unroll
-      for (int cc = 0; cc < NMARL_MAX_NA; ++cc) {
-        g[cc] = 0.f;
-        if (cc < n_a) {
-          const float pc = fminf(fmaxf(pi[cc], 1e-10f), 1.0f);
-          const float in_rng = (pi[cc] >= 1e-10f && pi[cc] <= 1.0f) ? 1.0f : 0.0f;
-          const float lp = logf(pc);
-          ent -= pi[cc] * lp;
-          g[cc] = k.e_coef * cs * (lp + in_rng);
-          if (cc == act) { g[cc] += -cs * Adv * in_rng / pc; lpa = lp; }
-          dot += pi[cc] * g[cc];
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+          if (cc < n_a) { logit[cc] += __ldg(P + ag.o_pi_b + cc); mx = fmaxf(mx, logit[cc]); }
+        float se = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+          if (cc < n_a) { pi[cc] = expf(logit[cc] - mx); se += pi[cc]; } else pi[cc] = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+          if (cc < n_a) { pi[cc] = pi[cc] / se; if (a.pi != nullptr) a.pi[row * n_a + cc] = pi[cc]; }
+      }
+      if (MODE == MODE_P && a.action != nullptr && a.sample_mode != NMARL_SAMPLE_NONE) {
+        int act = 0;
+        if (a.sample_mode == NMARL_SAMPLE_GREEDY) {
+          float best = pi[0];
+#pragma unroll
+          for (int cc = 1; cc < NMARL_MAX_NA; ++cc) if (cc < n_a && pi[cc] > best) { best = pi[cc]; act = cc; }
+        } else {
+          double u;
+          if (a.sample_mode == NMARL_SAMPLE_UNIFORM) u = a.uniforms[row];
+          else u = philox_u01(a.rng[0], a.rng[1] + a.rng_offset, (uint32_t)row, 0x41435431u);
+          double cdf[NMARL_MAX_NA];
+          double s = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < NMARL_MAX_NA; ++cc) { if (cc < n_a) s += (double)pi[cc]; cdf[cc] = s; }
+#pragma unroll
+          for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += ((cdf[cc] / s) <= u) ? 1 : 0;
+          act = min(act, n_a - 1);
         }
+        a.action[row] = act;
       }
-      float dl[8];
+      if (MODE != MODE_P) {
+        for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + a.act_in[(size_t)ag.nbr[s] * B + b]);
+        v += __ldg(P + ag.o_v_b);
+        if (a.v != nullptr) a.v[row] = v;
+      }
+      if (MODE == MODE_TRAIN) {
+        const int act = a.act_in[row];
+        const float R = k.Rs[row], Adv = k.Advs[row];
+        const float cs = k.loss_scale;
+        float g[NMARL_MAX_NA];
+        float ent = 0.f, dot = 0.f, lpa = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) dl[cc] = (cc < n_a) ? pi[cc] * (g[cc] - dot) : 0.f;
-      const float dvv = -k.v_coef * cs * (R - v);
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc) {
+          g[cc] = 0.f;
+          if (cc < n_a) {
+            const float pc = fminf(fmaxf(pi[cc], 1e-10f), 1.0f);
+            const float in_rng = (pi[cc] >= 1e-10f && pi[cc] <= 1.0f) ? 1.0f : 0.0f;
+            const float lp = logf(pc);
+            ent -= pi[cc] * lp;
+            g[cc] = k.e_coef * cs * (lp + in_rng);
+            if (cc == act) { g[cc] += -cs * Adv * in_rng / pc; lpa = lp; }
+            dot += pi[cc] * g[cc];
+          }
+        }
+        float dl[8];
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dl[cc] = dvv;
-      *reinterpret_cast<float4*>(k.sv_dlv + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-      *reinterpret_cast<float4*>(k.sv_dlv + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
-      l_pol = -lpa * Adv; l_val = (R - v) * (R - v); l_ent = ent;
+        for (int cc = 0; cc < 8; ++cc) dl[cc] = (cc < n_a) ? pi[cc] * (g[cc] - dot) : 0.f;
+        const float dvv = -k.v_coef * cs * (R - v);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dl[cc] = dvv;
+        *reinterpret_cast<float4*>(k.sv_dlv + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+        *reinterpret_cast<float4*>(k.sv_dlv + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+        l_pol = -lpa * Adv; l_val = (R - v) * (R - v); l_ent = ent;
+      }
     }
     if (VAR == NMARL_DIAL && MODE != MODE_V) {            // msg' = relu(h' W_mfc + b)   (utils.py:563-566)
-      float mo[64];
+      float mo[EW];
       enc_load(c, mo);
-      bias_act64(mo, P + ag.o_mfc_b, 0);
-      store64(a.msg_out + row * NH, mo);
+      bias_act(mo, P + ag.o_mfc_b + e0, 0);
+      store_vec<EW>(a.msg_out + row * NH + e0, mo);
     }
-    if (MODE == MODE_TRAIN) {
+    if (MODE == MODE_TRAIN && set == 0) {
       float vals[3] = {l_pol, l_val, l_ent};
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
         float x = vals[cc];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) red[cc][warp] = x;
+        if (lane == 0) red[cc][quarter] = x;
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == ROW_THREADS / 32) {
     // =================================== B producer ======================================================
     if (lane == 0) {
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(a.wpack);
@@ -541,10 +566,10 @@ __global__ void __launch_bounds__(192, 1) tc_cell_fwd_kernel(const __grid_consta
     lp[tid] = s;
     lp[4 + tid] = 0.f;                 // the second 64-row slot of this 128-row tile
   }
-  if (warp == 5) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
+  if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
 }
 
-constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 16 * 8 + 16 + MAX_KB * sizeof(KbEnt);
+constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 16 * 8 + 16 + MAX_KB * sizeof(KbEnt) + NSET * 128 * 8 * sizeof(float);
 
 template <int VAR, int MODE>
 int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
@@ -555,7 +580,7 @@ int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(k.a.B / 128, m->n_agent);
-  kern<<<grid, 192, TC_SMEM, st>>>(*m, k);
+  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   return 0;
 }
