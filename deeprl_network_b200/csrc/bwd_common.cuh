@@ -1,0 +1,18 @@
+// bwd_common.cuh -- argument block of one reverse step, shared by cell_bwd_kernel (FFMA, train.cu) and
+// tc_cell_bwd_kernel (tcgen05, tc_bwd.cu)
+#pragma once
+#include "common.cuh"
+
+struct BwdK {
+  int B, t, has_next;
+  const float* params; const float* wt;
+  const float* done_pre;        // [B] for step t
+  const float* sv_gates; const float* sv_sh; const float* sv_enc; const float* sv_dlv;   // step t
+  const float* c_prev; const float* c_cur;      // c_seq[t], c_seq[t+1]
+  const float* dh_in; const float* dc_in; const float* dmsg_in;       // produced by step t+1
+  float* dh_out; float* dc_out; float* dmsg_out;                       // consumed by step t-1
+  float* sv_dz; float* sv_dpre;                                        // step t
+  const float* wpack; int* tc_err;                                     // tcgen05 path (NULL -> FFMA)
+};
+
+int nmarl_tc_launch_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st);

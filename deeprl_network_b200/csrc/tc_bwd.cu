@@ -1,0 +1,272 @@
+// tc_bwd.cu -- tcgen05 version of one reverse BPTT step of the cell (K9): gate derivatives on CUDA
+// cores, then the dgrad GEMM  d[s | h^] = dz [wx;wh]^T  and the message-gradient GEMM
+// dm = dpre_m W_msg^T  as 3xTF32 tcgen05.mma with the A operand (dz, dpre_m) written straight from
+// registers into TMEM and the pre-packed transposed weights bulk-copied into swizzled shared memory.
+// Same CTA structure as tc_cell.cu (128 env rows x one agent, 4 warp-sets of row threads + producer +
+// MMA issuer); same inputs/outputs as cell_bwd_kernel (train.cu).
+#include "bwd_common.cuh"
+#include "tc_row.cuh"
+
+namespace {
+using namespace tcrow;
+
+template <int VAR>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid_constant__ nmarl_model m,
+                                                                    const __grid_constant__ BwdK k) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bst = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
+  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
+  uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
+  KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
+
+  const int i = blockIdx.y;
+  const nmarl_agent& ag = m.agent[i];
+  const int B = k.B, b0 = blockIdx.x * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_a = m.n_a, SD = m.s_dim;
+  const float* __restrict__ P = k.params;
+  constexpr int NGRP = (VAR == NMARL_NC) ? 4 : 2;
+  const int Km = (VAR == NMARL_IC3) ? NH : ag.n_nbr * NH;
+
+  if (tid == 0) {
+    for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
+    tc::mbar_init(enc_full, 1);
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+    int n = 0;
+    for (int kb = 0; kb < 8; ++kb) sched[n++] = make_kb(ag.tp_gT, SD + NH, NG, kb, 0, kb == 0, 0, kb == 7);
+    if (VAR != NMARL_IA2C && Km > 0)
+      for (int kb = 0; kb < 2; ++kb) sched[n++] = make_kb(ag.tp_mT, Km, NH, kb, 0, kb == 0, 0, kb == 1);
+    *n_kb_s = n;
+  }
+  if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_kb = *n_kb_s;
+
+  if (warp < ROW_THREADS / 32) {
+    RowCtx c;
+    const int set = warp >> 2, quarter = warp & 3, r = quarter * 32 + lane;
+    c.tmem = tmem; c.lane_base = (uint32_t)(quarter * 32) << 16;
+    c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.set = set; c.err = k.tc_err;
+    const int b = b0 + r;
+    const size_t row = (size_t)i * B + b;
+    const float nd = 1.0f - k.done_pre[b];
+    const int e0 = set * EW;                       // this thread's 16 hidden units
+    const float* gs = k.sv_gates + row * NG + e0;
+
+    // ---- total dh and dc for the thread's units --------------------------------------------------------------
+    float dh[EW], dct[EW];
+    {
+      const float4 d0 = *reinterpret_cast<const float4*>(k.sv_dlv + row * 8);
+      const float4 d1 = *reinterpret_cast<const float4*>(k.sv_dlv + row * 8 + 4);
+      const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float dv = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dv = dl[cc];
+#pragma unroll
+      for (int j = 0; j < EW; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc)
+          if (cc < n_a) s = fmaf(dl[cc], __ldg(P + ag.o_pi_w + (e0 + j) * n_a + cc), s);
+        dh[j] = fmaf(dv, __ldg(P + ag.o_v_w + e0 + j), s);
+        dct[j] = 0.f;
+      }
+      if (k.has_next) {
+#pragma unroll
+        for (int q = 0; q < EW / 4; ++q) {
+          const float4 r4 = *reinterpret_cast<const float4*>(k.dh_in + row * NH + e0 + 4 * q);
+          dh[4 * q] += r4.x; dh[4 * q + 1] += r4.y; dh[4 * q + 2] += r4.z; dh[4 * q + 3] += r4.w;
+          const float4 c4 = *reinterpret_cast<const float4*>(k.dc_in + row * NH + e0 + 4 * q);
+          dct[4 * q] = c4.x; dct[4 * q + 1] = c4.y; dct[4 * q + 2] = c4.z; dct[4 * q + 3] = c4.w;
+        }
+        if (VAR == NMARL_NC || VAR == NMARL_IC3) {
+          for (int s = 0; s < ag.n_recv; ++s) {
+            const float* mp = k.dmsg_in + (((size_t)ag.recv_agent[s] * NMARL_MAX_NBR + ag.recv_slot[s]) * B + b) * NH + e0;
+#pragma unroll
+            for (int q = 0; q < EW / 4; ++q) {
+              const float4 m4 = *reinterpret_cast<const float4*>(mp + 4 * q);
+              dh[4 * q] += m4.x; dh[4 * q + 1] += m4.y; dh[4 * q + 2] += m4.z; dh[4 * q + 3] += m4.w;
+            }
+          }
+        }
+      }
+      // dc_t += dh * o * (1 - tanh(c_t)^2)
+#pragma unroll
+      for (int q = 0; q < EW / 4; ++q) {
+        const float4 go = *reinterpret_cast<const float4*>(gs + 2 * NH + 4 * q);
+        const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float tcv = tanhf(f4get(cc, j));
+          dct[4 * q + j] += dh[4 * q + j] * f4get(go, j) * (1.0f - tcv * tcv);
+        }
+      }
+    }
+    // ---- gate derivatives, gate by gate = k-block pair by k-block pair of the dgrad A operand -----------------
+    float* zo = k.sv_dz + row * NG + e0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float dz[EW];
+#pragma unroll
+      for (int q = 0; q < EW / 4; ++q) {
+        if (g == 0 || g == 3) {
+          const float4 gi = *reinterpret_cast<const float4*>(gs + 0 * NH + 4 * q);
+          const float4 gu = *reinterpret_cast<const float4*>(gs + 3 * NH + 4 * q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ig = f4get(gi, j), ug = f4get(gu, j);
+            dz[4 * q + j] = (g == 0) ? dct[4 * q + j] * ug * ig * (1.0f - ig) : dct[4 * q + j] * ig * (1.0f - ug * ug);
+          }
+        } else if (g == 1) {
+          const float4 gf = *reinterpret_cast<const float4*>(gs + 1 * NH + 4 * q);
+          const float4 cp = *reinterpret_cast<const float4*>(k.c_prev + row * NH + e0 + 4 * q);
+          float dcp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float fg = f4get(gf, j);
+            dz[4 * q + j] = dct[4 * q + j] * (f4get(cp, j) * nd) * fg * (1.0f - fg);
+            dcp[j] = dct[4 * q + j] * fg * nd;
+          }
+          *reinterpret_cast<float4*>(k.dc_out + row * NH + e0 + 4 * q) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+        } else {
+          const float4 go = *reinterpret_cast<const float4*>(gs + 2 * NH + 4 * q);
+          const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float og = f4get(go, j), tcv = tanhf(f4get(cc, j));
+            dz[4 * q + j] = dh[4 * q + j] * tcv * og * (1.0f - og);
+          }
+        }
+      }
+      store_vec<EW>(zo + g * NH, dz);
+      produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
+    }
+
+    // ---- dgrad result: d[s | h^] -------------------------------------------------------------------------------
+    tc::mbar_wait(acc_full, 0, k.tc_err, 13);
+    tc::fence_after_sync();
+    float dpm[EW];
+#pragma unroll
+    for (int j = 0; j < EW; ++j) dpm[j] = 0.f;
+    float* dp = k.sv_dpre + row * 192 + e0;
+#pragma unroll
+    for (int gp = 0; gp < NGRP; ++gp) {
+      float d[EW];
+#pragma unroll
+      for (int p = 0; p < EW / 8; ++p) {
+        float t[8];
+        tc::tmem_ld8(tmem + c.lane_base + ACC_COL + gp * NH + e0 + 8 * p, t);
+        tc::wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[8 * p + j] = t[j];
+      }
+      if (gp == NGRP - 1) {                    // own recurrent gradient, done-masked
+#pragma unroll
+        for (int j = 0; j < EW; ++j) d[j] *= nd;
+        store_vec<EW>(k.dh_out + row * NH + e0, d);
+      } else if (VAR == NMARL_NC || VAR == NMARL_IA2C) {
+        float sv[EW];
+#pragma unroll
+        for (int q = 0; q < EW / 4; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(k.sv_sh + row * (SD + NH) + gp * NH + e0 + 4 * q);
+          sv[4 * q] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < EW; ++j) d[j] = sv[j] > 0.f ? d[j] : 0.f;
+        store_vec<EW>(dp + gp * NH, d);
+        if (VAR == NMARL_NC && gp == 2) {
+#pragma unroll
+          for (int j = 0; j < EW; ++j) dpm[j] = d[j];
+        }
+      } else {                                  // IC3 / DIAL: one 64-wide s
+        float hx[EW], hm[EW], o[EW];
+#pragma unroll
+        for (int q = 0; q < EW / 4; ++q) {
+          const float4 a4 = *reinterpret_cast<const float4*>(k.sv_enc + row * 128 + e0 + 4 * q);
+          hx[4 * q] = a4.x; hx[4 * q + 1] = a4.y; hx[4 * q + 2] = a4.z; hx[4 * q + 3] = a4.w;
+          if (VAR == NMARL_DIAL) {
+            const float4 b4 = *reinterpret_cast<const float4*>(k.sv_enc + row * 128 + NH + e0 + 4 * q);
+            hm[4 * q] = b4.x; hm[4 * q + 1] = b4.y; hm[4 * q + 2] = b4.z; hm[4 * q + 3] = b4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < EW; ++j) {
+          if (VAR == NMARL_IC3) { o[j] = d[j] * (1.0f - hx[j] * hx[j]); dpm[j] = d[j]; }
+          else { o[j] = hx[j] > 0.f ? d[j] : 0.f; dpm[j] = hm[j] > 0.f ? d[j] : 0.f; }
+        }
+        store_vec<EW>(dp, o);
+        store_vec<EW>(dp + NH, dpm);
+      }
+    }
+    tc::fence_before_sync();
+    // ---- message gradient dm = dpre_m W_msg^T, one 64-wide block per neighbour slot --------------------------
+    if (VAR != NMARL_IA2C && Km > 0) {
+      produce_act(c, dpm);
+      tc::mbar_wait(acc_full, 1, k.tc_err, 14);
+      tc::fence_after_sync();
+      const int nblk = (VAR == NMARL_IC3) ? 1 : ag.n_nbr;
+      for (int s = 0; s < nblk; ++s) {
+        float d[EW];
+#pragma unroll
+        for (int p = 0; p < EW / 8; ++p) {
+          float t[8];
+          tc::tmem_ld8(tmem + c.lane_base + ACC_COL + s * NH + e0 + 8 * p, t);
+          tc::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[8 * p + j] = t[j];
+        }
+        if (VAR == NMARL_IC3) {
+          const float nn = (float)ag.n_nbr;
+#pragma unroll
+          for (int j = 0; j < EW; ++j) d[j] /= nn;
+          for (int s2 = 0; s2 < ag.n_nbr; ++s2) store_vec<EW>(k.dmsg_out + (((size_t)i * NMARL_MAX_NBR + s2) * B + b) * NH + e0, d);
+        } else {
+          store_vec<EW>(k.dmsg_out + (((size_t)i * NMARL_MAX_NBR + s) * B + b) * NH + e0, d);
+        }
+      }
+      tc::fence_before_sync();
+    }
+  } else if (warp == ROW_THREADS / 32) {
+    if (lane == 0) producer_loop(sched, n_kb, bst, b_full, b_empty, k.wpack, k.tc_err);
+  } else {
+    if (lane == 0) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, k.tc_err);
+  }
+  __syncthreads();
+  if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
+}
+
+template <int VAR>
+int launch_tc_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
+  auto kern = tc_cell_bwd_kernel<VAR>;
+  static bool configured = false;
+  if (!configured) {
+    NMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    configured = true;
+  }
+  dim3 grid(k.B / 128, m->n_agent);
+  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k);
+  NMARL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int nmarl_tc_launch_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
+  switch (m->variant) {
+    case NMARL_IA2C: return launch_tc_bwd<NMARL_IA2C>(m, k, st);
+    case NMARL_NC: return launch_tc_bwd<NMARL_NC>(m, k, st);
+    case NMARL_IC3: return launch_tc_bwd<NMARL_IC3>(m, k, st);
+    case NMARL_DIAL: return launch_tc_bwd<NMARL_DIAL>(m, k, st);
+  }
+  nmarl_set_error("unknown variant %d", m->variant);
+  return 1;
+}

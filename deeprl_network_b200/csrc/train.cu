@@ -10,7 +10,7 @@
 //      (receiver, slot) and GATHERED by the sender at step t-1 (deterministic; the transpose of
 //      the forward neighbour gather, what tf.gradients does through tf.boolean_mask)
 //   4. weight gradients as split-K "A^T D" GEMMs over all (t, env) rows + fixed-order reduce
-#include "common.cuh"
+#include "bwd_common.cuh"
 
 int nmarl_check_model(const nmarl_model* m);
 int nmarl_launch_train_fwd(const nmarl_model* m, const nmarl_fwd_args* a, const float* Rs, const float* Advs,
@@ -83,17 +83,6 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 }
 
 // ============================ K9: one reverse step of the cell ==================================
-struct BwdK {
-  int B, t, has_next;
-  const float* params; const float* wt;
-  const float* done_pre;        // [B] for step t
-  const float* sv_gates; const float* sv_sh; const float* sv_enc; const float* sv_dlv;   // step t
-  const float* c_prev; const float* c_cur;      // c_seq[t], c_seq[t+1]
-  const float* dh_in; const float* dc_in; const float* dmsg_in;       // produced by step t+1
-  float* dh_out; float* dc_out; float* dmsg_out;                       // consumed by step t-1
-  float* sv_dz; float* sv_dpre;                                        // step t
-};
-
 template <int VAR, int BM, int TY>
 __global__ void __launch_bounds__(16 * TY) cell_bwd_kernel(const __grid_constant__ nmarl_model m,
                                                           const __grid_constant__ BwdK k) {
@@ -784,7 +773,10 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     }
     k.sv_dz = a->sv_dz + (size_t)t * nb * NG;
     k.sv_dpre = a->sv_dpre + (size_t)t * nb * 192;
+    k.wpack = a->wpack; k.tc_err = a->tc_err;
     int rc = 0;
+    if (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32) rc = nmarl_tc_launch_bwd(m, k, st);
+    else
     switch (m->variant) {
       case NMARL_IA2C: rc = launch_bwd<NMARL_IA2C>(m, k, st); break;
       case NMARL_NC: rc = launch_bwd<NMARL_NC>(m, k, st); break;

@@ -41,13 +41,14 @@ def _oracle_backward(orc, lay, batch, lr=5e-4, apply=False, hp=HP):
 
 
 @pytest.mark.parametrize('variant', VARIANTS)
-@pytest.mark.parametrize('T,B', [(6, 1), (5, 37), (3, 130), (3, 128)])    # B=128: tcgen05 training forward
+@pytest.mark.parametrize('T,B', [(6, 1), (5, 37), (3, 130), (3, 128), (4, 256)])    # B % 128 == 0: tcgen05 forward + backward
 def test_gradients_match_oracle_autograd(variant, T, B):
     eng, orc, lay, params = make_pair(variant, B, T=T, dtype=torch.float64)
     batch = _batch(eng, lay, T, B)
     summ = _oracle_backward(orc, lay, batch)
     eng.backward()
     torch.cuda.synchronize()
+    eng.check_tc()
     g = lay.unpack(eng.grads.cpu().numpy())
     worst = 0.0
     for name in orc.names:
