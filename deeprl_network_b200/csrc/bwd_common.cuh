@@ -13,6 +13,12 @@ struct BwdK {
   float* dh_out; float* dc_out; float* dmsg_out;                       // consumed by step t-1
   float* sv_dz; float* sv_dpre;                                        // step t
   const float* wpack; int* tc_err;                                     // tcgen05 path (NULL -> FFMA)
+  float* dzT;                                                          // step t: [N][B/32][hi|lo][256][32] tiles or NULL
 };
 
 int nmarl_tc_launch_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st);
+int nmarl_tc_wgrad_splits(int n_agent);
+int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m);
+int nmarl_tc_launch_gate_wgrad(const nmarl_model* m, int B, int T, const float* sv_sh, const float* dzT, const float* sv_dz,
+                               float* ws, int* err, int* splits_out, cudaStream_t st);
+int nmarl_tc_launch_bias_reduce(const nmarl_model* m, const float* ws, int splits, float* grads, cudaStream_t st);

@@ -148,6 +148,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         }
       }
       store_vec<EW>(zo + g * NH, dz);
+      if (k.dzT != nullptr) {                 // dz^T tile for the tensor-core wgrad: K-major over rows, hi | lo
+        uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * 256 * 128);
+#pragma unroll
+        for (int j = 0; j < EW; ++j) {
+          const uint32_t off = tc::sw128_offset((uint32_t)(g * NH + e0 + j), (uint32_t)lane);
+          const float hi = __uint_as_float(__float_as_uint(dz[j]) & 0xFFFFE000u);
+          *reinterpret_cast<float*>(tile + off) = hi;
+          *reinterpret_cast<float*>(tile + 256 * 128 + off) = dz[j] - hi;
+        }
+      }
       produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
     }
 

@@ -682,7 +682,9 @@ extern "C" int64_t nmarl_ws_floats(const nmarl_model* m, int B, int T) {
   int64_t enc = (int64_t)splits * m->n_agent * (m->km_pad + m->kx_pad + 1) * NH;
   int64_t head = (int64_t)head_splits((long)B * T) * m->n_agent * HEAD_WS;
   int64_t r = gate > enc ? gate : enc;
-  return r > head ? r : head;
+  r = r > head ? r : head;
+  const int64_t tcw = nmarl_tc_wgrad_ws_floats(m);
+  return r > tcw ? r : tcw;
 }
 
 extern "C" int nmarl_nstep_return_adv(int n_agent, int B, int T, int NR, const double* reward, const float* value,
@@ -774,8 +776,10 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     k.sv_dz = a->sv_dz + (size_t)t * nb * NG;
     k.sv_dpre = a->sv_dpre + (size_t)t * nb * 192;
     k.wpack = a->wpack; k.tc_err = a->tc_err;
+    const bool use_tc = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
+    k.dzT = (use_tc && a->sv_dzT) ? a->sv_dzT + (size_t)t * N * (B / 32) * (2 * 256 * 32) : nullptr;
     int rc = 0;
-    if (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32) rc = nmarl_tc_launch_bwd(m, k, st);
+    if (use_tc) rc = nmarl_tc_launch_bwd(m, k, st);
     else
     switch (m->variant) {
       case NMARL_IA2C: rc = launch_bwd<NMARL_IA2C>(m, k, st); break;
@@ -794,8 +798,19 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   // 3. weight gradients
   int Ka[NMARL_MAX_AGENT], ow[NMARL_MAX_AGENT], ob[NMARL_MAX_AGENT];
   const int LDI = m->kx_pad + m->kp_pad + m->km_pad;
+  const bool tc_wg = (a->wpack != nullptr && a->sv_dzT != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32 && SD + NH == 256);
   for (int i = 0; i < N; ++i) { Ka[i] = SD + NH; ow[i] = m->agent[i].o_wxh; ob[i] = m->agent[i].o_b; }
-  if (run_wgrad(m, a, 4, a->sv_sh, SD + NH, 0, a->sv_dz, NG, 0, Ka, ow, ob, st)) return 1;
+  if (tc_wg) {
+    NMARL_CHECK(nmarl_tc_wgrad_ws_floats(m) <= a->ws_floats, "tc wgrad: workspace too small");
+    int splits = 0;
+    if (nmarl_tc_launch_gate_wgrad(m, B, T, a->sv_sh, a->sv_dzT, a->sv_dz, a->ws, a->tc_err, &splits, st)) return 1;
+    WgRedK r{};
+    r.N = N; r.splits = splits; r.ka_max = 256; r.nd = NG; r.ws = a->ws; r.grads = a->grads;
+    for (int i = 0; i < N; ++i) { r.Ka[i] = 256; r.o_w[i] = ow[i]; r.o_b[i] = -1; }
+    wgrad_reduce_kernel<<<dim3((257 * NG + 255) / 256, N), 256, 0, st>>>(r);
+    NMARL_LAUNCH_CHECK();
+    if (nmarl_tc_launch_bias_reduce(m, a->ws, splits, a->grads, st)) return 1;
+  } else if (run_wgrad(m, a, 4, a->sv_sh, SD + NH, 0, a->sv_dz, NG, 0, Ka, ow, ob, st)) return 1;
   for (int i = 0; i < N; ++i) { Ka[i] = m->agent[i].x_nsrc * m->agent[i].x_w; ow[i] = m->agent[i].o_w_ob; ob[i] = m->agent[i].o_b_ob; }
   if (run_wgrad(m, a, 1, a->sv_xin, LDI, 0, a->sv_dpre, 192, 0, Ka, ow, ob, st)) return 1;
   if (m->variant == NMARL_NC) {

@@ -196,6 +196,7 @@ typedef struct {
   float* grads;
   const float* wpack;        /* packed tensor-core operands or NULL (see nmarl_fwd_args)            */
   int32_t* tc_err;
+  float* sv_dzT;             /* tensor-core path: dz^T as [T][N][B/32][hi|lo][256][32] swizzled tiles  */
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */
