@@ -52,7 +52,8 @@ class FwdArgs(C.Structure):
                 ('c_out', C.c_void_p), ('h_out', C.c_void_p), ('msg_out', C.c_void_p),
                 ('pi', C.c_void_p), ('action', C.c_void_p), ('sample_mode', C.c_int32),
                 ('uniforms', C.c_void_p), ('rng', C.c_void_p), ('rng_offset', C.c_uint64),
-                ('act_in', C.c_void_p), ('v', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p)]
+                ('act_in', C.c_void_p), ('v', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
+                ('sv_xin', C.c_void_p), ('sv_sh', C.c_void_p), ('sv_gates', C.c_void_p), ('sv_enc', C.c_void_p)]
 
 
 class BwdArgs(C.Structure):
@@ -74,7 +75,8 @@ _lib = None
 EXPORTS = ['nmarl_last_error', 'nmarl_version', 'nmarl_sizeof_model', 'nmarl_sizeof_agent', 'nmarl_sizeof_cacc_cfg',
            'nmarl_cacc_reset', 'nmarl_cacc_step', 'nmarl_pack_weights', 'nmarl_policy_step_p', 'nmarl_policy_step_v', 'nmarl_dial_msg',
            'nmarl_rng_advance', 'nmarl_nstep_return_adv', 'nmarl_loss_tiles', 'nmarl_ws_floats',
-           'nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt', 'nmarl_clip_rmsprop_step']
+           'nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt', 'nmarl_a2c_train_heads',
+           'nmarl_clip_rmsprop_step']
 
 
 def lib():
@@ -99,7 +101,7 @@ def lib():
     L.nmarl_nstep_return_adv.argtypes = [I, I, I, I, P, P, P, P, I, D, D, D, D, P, P, I, P, P, P]
     L.nmarl_loss_tiles.argtypes = [C.POINTER(Model), I]
     L.nmarl_ws_floats.argtypes = [C.POINTER(Model), I, I]
-    for fn in ('nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt'):
+    for fn in ('nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt', 'nmarl_a2c_train_heads'):
         getattr(L, fn).argtypes = [C.POINTER(Model), C.POINTER(BwdArgs), P]
     L.nmarl_clip_rmsprop_step.argtypes = [C.POINTER(Model), P, P, P, P, F, F, F, P, P, P]
     assert L.nmarl_sizeof_model() == C.sizeof(Model), 'nmarl_model layout mismatch'

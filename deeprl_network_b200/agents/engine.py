@@ -83,6 +83,8 @@ class PolicyEngine:
         else:
             self.dist_dev, self.alpha_pow = None, None
         self._train_ready = False
+        self.saved_rollout = False
+        self.fuse_save = os.environ.get('NMARL_NO_FUSE_SAVE', '0') != '1'
         self.T_cur = T
         self.launches = 0
         self.repack()
@@ -177,6 +179,13 @@ class PolicyEngine:
         T = self.T if n_step is None else int(n_step)
         self.T_cur = T
         mode = {'philox': L.SAMPLE_PHILOX, 'uniform': L.SAMPLE_UNIFORM, 'greedy': L.SAMPLE_GREEDY}[sample]
+        # tensor-core path: the rollout p-calls save the activations BPTT needs (same inputs, same weights as
+        # the reference's separate training forward => same numbers), and the LSTM state lives in h_seq/c_seq
+        self.saved_rollout = bool(self.use_tc and self.fuse_save and bootstrap and sample != 'greedy' and T == self.T)
+        if self.saved_rollout:
+            self._alloc_train()
+            self._rollout_saved(env, mode, uniforms, T)
+            return
         for t in range(T):
             obs, fp, done = self.obs_buf[t], self.fp_buf[t], self.done_buf[t]
             self.step_p(obs, fp, done, self.fp_buf[t + 1], self.act_buf[t], mode,
@@ -191,6 +200,51 @@ class PolicyEngine:
             self.step_p(self.obs_buf[T], self.fp_buf[T], self.done_buf[T], self.boot_pi, self.boot_act, mode,
                         None if uniforms is None else uniforms[T], rng_offset=T)
             self.step_v(self.obs_buf[T], self.fp_buf[T], self.done_buf[T], self.boot_act, self.R_end)
+        if mode == L.SAMPLE_PHILOX:
+            L.check(L.lib().nmarl_rng_advance(L.ptr(self.rng), T + 1, L.stream()), 'nmarl_rng_advance')
+            self.launches += 1
+
+    def _seq_call(self, t, obs, fp, done, which, **kw):
+        """p- or v-call with the state taken from / written to slot t / t+1 of the saved sequences."""
+        a = L.FwdArgs()
+        a.B = self.B
+        a.params, a.obs, a.fp, a.done = L.ptr(self.params), L.ptr(obs), L.ptr(fp), L.ptr(done)
+        a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
+        ms = self.msg_seq
+        if which == 'p':
+            a.c_in, a.h_in, a.msg_in = L.ptr(self.c_seq[t]), L.ptr(self.h_seq[t]), L.ptr(None if ms is None else ms[t])
+            a.c_out, a.h_out, a.msg_out = L.ptr(self.c_seq[t + 1]), L.ptr(self.h_seq[t + 1]), L.ptr(None if ms is None else ms[t + 1])
+            a.pi, a.action, a.sample_mode = L.ptr(kw['pi']), L.ptr(kw['action']), kw['mode']
+            a.uniforms, a.rng, a.rng_offset = L.ptr(kw.get('uniforms')), L.ptr(self.rng), t
+            if kw.get('save', False):
+                a.sv_xin, a.sv_sh, a.sv_gates = L.ptr(self.sv_xin[t]), L.ptr(self.sv_sh[t]), L.ptr(self.sv_gates[t])
+                a.sv_enc = L.ptr(None if self.sv_enc is None else self.sv_enc[t])
+            L.check(L.lib().nmarl_policy_step_p(C.byref(self.model), C.byref(a), L.stream()), 'nmarl_policy_step_p')
+        else:
+            a.c_in, a.h_in, a.msg_in = L.ptr(self.c_seq[t + 1]), L.ptr(self.h_seq[t + 1]), L.ptr(None if ms is None else ms[t + 1])
+            a.act_in, a.v = L.ptr(kw['act']), L.ptr(kw['v'])
+            L.check(L.lib().nmarl_policy_step_v(C.byref(self.model), C.byref(a), L.stream()), 'nmarl_policy_step_v')
+        self.launches += 1
+
+    def _rollout_saved(self, env, mode, uniforms, T):
+        self.h_seq[0].copy_(self.h[self.cur]); self.c_seq[0].copy_(self.c[self.cur])
+        if self.msg_seq is not None:
+            self.msg_seq[0].copy_(self.msg[self.cur])
+        for t in range(T):
+            obs, fp, done = self.obs_buf[t], self.fp_buf[t], self.done_buf[t]
+            self._seq_call(t, obs, fp, done, 'p', pi=self.fp_buf[t + 1], action=self.act_buf[t], mode=mode,
+                           uniforms=None if uniforms is None else uniforms[t], save=True)
+            self._seq_call(t, obs, fp, done, 'v', act=self.act_buf[t], v=self.val_buf[t])
+            env.step_device(self.act_buf[t], obs_out=self.obs_buf[t + 1], reward_out=self.rew_buf[t],
+                            greward_out=self.grew_buf[t], done_out=self.done_buf[t + 1])
+            self.launches += 1
+        # bootstrap (Q2): one more p-call (state advanced into slot T+1, not saved for BPTT) + v-call
+        self._seq_call(T, self.obs_buf[T], self.fp_buf[T], self.done_buf[T], 'p', pi=self.boot_pi, action=self.boot_act,
+                       mode=mode, uniforms=None if uniforms is None else uniforms[T])
+        self._seq_call(T, self.obs_buf[T], self.fp_buf[T], self.done_buf[T], 'v', act=self.boot_act, v=self.R_end)
+        self.h[self.cur].copy_(self.h_seq[T + 1]); self.c[self.cur].copy_(self.c_seq[T + 1])
+        if self.msg_seq is not None:
+            self.msg[self.cur].copy_(self.msg_seq[T + 1])
         if mode == L.SAMPLE_PHILOX:
             L.check(L.lib().nmarl_rng_advance(L.ptr(self.rng), T + 1, L.stream()), 'nmarl_rng_advance')
             self.launches += 1
@@ -219,8 +273,8 @@ class PolicyEngine:
         lay, N, B, T, dev = self.layout, self.N, self.B, self.T, self.device
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
-        self.h_seq, self.c_seq = z(T + 1, N, B, NH), z(T + 1, N, B, NH)
-        self.msg_seq = z(T + 1, N, B, NH) if self.variant == 'ma2c_dial' else None
+        self.h_seq, self.c_seq = z(T + 2, N, B, NH), z(T + 2, N, B, NH)       # +1 slot for the bootstrap p-call
+        self.msg_seq = z(T + 2, N, B, NH) if self.variant == 'ma2c_dial' else None
         self.sv_xin = z(T, N, B, lay.ld_in)
         self.sv_sh = z(T, N, B, lay.s_dim + NH)
         self.sv_gates = z(T, N, B, 4 * NH)
@@ -261,6 +315,13 @@ class PolicyEngine:
         (local sum over this rank's envs, already scaled by 1/(T * B_total))."""
         T = self.T_cur
         a = self._bwd_args(T)
+        if getattr(self, 'saved_rollout', False):
+            # activations, h_seq / c_seq (slot 0 == states_bw) were written by the rollout p-calls
+            L.check(L.lib().nmarl_a2c_train_heads(C.byref(self.model), C.byref(a), L.stream()), 'nmarl_a2c_train_heads')
+            L.check(L.lib().nmarl_a2c_bptt(C.byref(self.model), C.byref(a), L.stream()), 'nmarl_a2c_bptt')
+            self.launches += 2 * T + 16
+            self.saved_rollout = False
+            return
         self.h_seq[0].copy_(self.h_bw); self.c_seq[0].copy_(self.c_bw)
         if self.variant == 'ma2c_dial':
             L.check(L.lib().nmarl_dial_msg(C.byref(self.model), self.B, L.ptr(self.params), L.ptr(self.h_seq[0]),

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { MODE_P = 0, MODE_V = 1, MODE_TRAIN = 2 };
+enum { MODE_P = 0, MODE_V = 1, MODE_TRAIN = 2, MODE_PS = 3 };   // PS: p-call that also saves activations for BPTT
 
 struct FwdK {
   nmarl_fwd_args a;

@@ -475,6 +475,13 @@ extern "C" int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a
   NMARL_CHECK(a->sample_mode != NMARL_SAMPLE_PHILOX || a->rng, "policy_step_p: rng state required");
   FwdK k{};
   k.a = *a;
+  if (a->sv_sh != nullptr) {                 // rollout p-call that also saves activations for BPTT
+    NMARL_CHECK(nmarl_tc_fwd_supported(m, a), "policy_step_p: activation saving needs the tensor-core path (B %% 128 == 0, wpack)");
+    NMARL_CHECK(a->sv_xin && a->sv_gates, "policy_step_p: sv_xin / sv_gates missing");
+    NMARL_CHECK((m->variant != NMARL_IC3 && m->variant != NMARL_DIAL) || a->sv_enc, "policy_step_p: sv_enc missing");
+    k.sv_xin = a->sv_xin; k.sv_sh = a->sv_sh; k.sv_gates = a->sv_gates; k.sv_enc = a->sv_enc;
+    return nmarl_tc_launch_fwd(m, k, MODE_PS, (cudaStream_t)stream);
+  }
   return dispatch_fwd<MODE_P>(m, k, (cudaStream_t)stream);
 }
 

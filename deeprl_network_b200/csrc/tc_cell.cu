@@ -30,6 +30,8 @@ using namespace tcrow;
 template <int VAR, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid_constant__ nmarl_model m,
                                                                     const __grid_constant__ FwdK k) {
+  constexpr bool SAVE = (MODE == MODE_TRAIN || MODE == MODE_PS);   // store activations for BPTT
+  constexpr bool SAMPLE = (MODE == MODE_P || MODE == MODE_PS);     // p-call: sample actions
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     const size_t row = (size_t)i * B + b;
     const float nd = 1.0f - a.done[b];
     const int LDI = m.kx_pad + m.kp_pad + m.km_pad;
-    float* xin_row = (MODE == MODE_TRAIN) ? k.sv_xin + row * LDI : nullptr;
-    float* sh_row = (MODE == MODE_TRAIN) ? k.sv_sh + row * (SD + NH) : nullptr;
+    float* xin_row = SAVE ? k.sv_xin + row * LDI : nullptr;
+    float* sh_row = SAVE ? k.sv_sh + row * (SD + NH) : nullptr;
     const int c0 = set * W;             // this thread's columns inside every 32-wide input k-block
     const int e0 = set * EW;            // this thread's hidden units / encoder columns
 
@@ -127,16 +129,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         }
         xv[j] = val;
       }
-      if (MODE == MODE_TRAIN && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
+      if (SAVE && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
       produce_in(c, xv);
     }
     float s0[EW];                       // this thread's slice of the encoder output being assembled
     enc_load(c, s0);
     bias_act(s0, P + ag.o_b_ob + e0, VAR == NMARL_IC3 ? 1 : 0);
-    if (MODE == MODE_TRAIN && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
+    if (SAVE && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
 
     if (VAR == NMARL_NC) {
-      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+      if (SAVE) store_vec<EW>(sh_row + e0, s0);
       produce_act(c, s0);
       // ---- fingerprint encoder ----
       {
@@ -152,17 +154,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           }
           pv[j] = val;
         }
-        if (MODE == MODE_TRAIN && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
+        if (SAVE && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
         produce_in(c, pv);
       }
       enc_load(c, s0);
       bias_act(s0, P + ag.o_b_fp + e0, 0);
-      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + NH + e0, s0);
+      if (SAVE) store_vec<EW>(sh_row + NH + e0, s0);
       produce_act(c, s0);
     }
     if (VAR != NMARL_IA2C) {
       // ---- message encoder: neighbours' UN-masked h (NC), their mean (IC3) or their messages (DIAL) ----
-      float* xm = (MODE == MODE_TRAIN) ? xin_row + m.kx_pad + m.kp_pad : nullptr;
+      float* xm = SAVE ? xin_row + m.kx_pad + m.kp_pad : nullptr;
       if (VAR == NMARL_IC3) {
         const float nn = (float)ag.n_nbr;
 #pragma unroll
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           }
 #pragma unroll
           for (int j = 0; j < W; ++j) mv[j] /= nn;
-          if (MODE == MODE_TRAIN) store_vec<W>(xm + hb * 32 + c0, mv);
+          if (SAVE) store_vec<W>(xm + hb * 32 + c0, mv);
           produce_in(c, mv);
         }
       } else {
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
               const float4 w = *reinterpret_cast<const float4*>(hp + hb * 32 + 4 * q);
               mv[4 * q] = w.x; mv[4 * q + 1] = w.y; mv[4 * q + 2] = w.z; mv[4 * q + 3] = w.w;
             }
-            if (MODE == MODE_TRAIN) store_vec<W>(xm + s * NH + hb * 32 + c0, mv);
+            if (SAVE) store_vec<W>(xm + s * NH + hb * 32 + c0, mv);
             produce_in(c, mv);
           }
         }
-        if (MODE == MODE_TRAIN) {
+        if (SAVE) {
           float z[W];
 #pragma unroll
           for (int j = 0; j < W; ++j) z[j] = 0.f;
@@ -210,17 +212,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       enc_load(c, s1);
       if (VAR == NMARL_NC) {
         bias_act(s1, P + ag.o_b_msg + e0, 0);
-        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + 2 * NH + e0, s1);
+        if (SAVE) store_vec<EW>(sh_row + 2 * NH + e0, s1);
         produce_act(c, s1);
       } else if (VAR == NMARL_IC3) {
         bias_act(s1, P + ag.o_b_msg + e0, 2);
 #pragma unroll
         for (int j = 0; j < EW; ++j) s0[j] += s1[j];
-        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+        if (SAVE) store_vec<EW>(sh_row + e0, s0);
         produce_act(c, s0);
       } else {  // DIAL
         bias_act(s1, P + ag.o_b_msg + e0, 0);
-        if (MODE == MODE_TRAIN) store_vec<EW>(k.sv_enc + row * 128 + NH + e0, s1);
+        if (SAVE) store_vec<EW>(k.sv_enc + row * 128 + NH + e0, s1);
         int am = 0;
         {
           const float* pr = a.fp + row * n_a;
@@ -229,11 +231,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         }
 #pragma unroll
         for (int j = 0; j < EW; ++j) s0[j] = (s0[j] + s1[j]) + ((e0 + j) == am ? 1.0f : 0.0f);
-        if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+        if (SAVE) store_vec<EW>(sh_row + e0, s0);
         produce_act(c, s0);
       }
     } else {
-      if (MODE == MODE_TRAIN) store_vec<EW>(sh_row + e0, s0);
+      if (SAVE) store_vec<EW>(sh_row + e0, s0);
       produce_act(c, s0);
     }
     // ---- own h (done-masked): two input k-blocks --------------------------------------------------------------
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
         hv[4 * q] = w.x * nd; hv[4 * q + 1] = w.y * nd; hv[4 * q + 2] = w.z * nd; hv[4 * q + 3] = w.w * nd;
       }
-      if (MODE == MODE_TRAIN) store_vec<W>(sh_row + SD + hb * 32 + c0, hv);
+      if (SAVE) store_vec<W>(sh_row + SD + hb * 32 + c0, hv);
       produce_in(c, hv);
     }
 
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         store_vec<8>(a.c_out + row * NH + u0, cn);
         store_vec<8>(a.h_out + row * NH + u0, hn);
       }
-      if (MODE == MODE_TRAIN) {
+      if (SAVE) {
         float* gs = k.sv_gates + row * NG + u0;
         store_vec<8>(gs + 0 * NH, gi); store_vec<8>(gs + 1 * NH, gf); store_vec<8>(gs + 2 * NH, go); store_vec<8>(gs + 3 * NH, gu);
       }
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
             if (cc < n_a) logit[cc] = fmaf(hn[x], __ldg(P + ag.o_pi_w + (u0 + x) * n_a + cc), logit[cc]);
       }
-      if (MODE != MODE_P) {
+      if (!SAMPLE) {
 #pragma unroll
         for (int x = 0; x < 8; ++x) v = fmaf(hn[x], __ldg(P + ag.o_v_w + u0 + x), v);
       }
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
           if (cc < n_a) { pi[cc] = pi[cc] / se; if (a.pi != nullptr) a.pi[row * n_a + cc] = pi[cc]; }
       }
-      if (MODE == MODE_P && a.action != nullptr && a.sample_mode != NMARL_SAMPLE_NONE) {
+      if (SAMPLE && a.action != nullptr && a.sample_mode != NMARL_SAMPLE_NONE) {
         int act = 0;
         if (a.sample_mode == NMARL_SAMPLE_GREEDY) {
           float best = pi[0];
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         }
         a.action[row] = act;
       }
-      if (MODE != MODE_P) {
+      if (!SAMPLE) {
         for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + a.act_in[(size_t)ag.nbr[s] * B + b]);
         v += __ldg(P + ag.o_v_b);
         if (a.v != nullptr) a.v[row] = v;
@@ -452,6 +454,7 @@ int launch_tc_mode(const nmarl_model* m, const FwdK& k, int mode, cudaStream_t s
   switch (mode) {
     case MODE_P: return launch_tc<VAR, MODE_P>(m, k, st);
     case MODE_V: return launch_tc<VAR, MODE_V>(m, k, st);
+    case MODE_PS: return launch_tc<VAR, MODE_PS>(m, k, st);
     default: return launch_tc<VAR, MODE_TRAIN>(m, k, st);
   }
 }

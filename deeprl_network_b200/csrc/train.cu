@@ -594,6 +594,97 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
   }
 }
 
+// Heads + A2C loss terms + d(loss)/d(logits, v) from the saved h sequence (thread == env row); used when the
+// rollout already saved the cell activations.  Same arithmetic as the TRAIN epilogue of the forward kernels.
+struct HeadFwdK {
+  int B, loss_tiles;
+  const float* params; const float* h1; const int32_t* act; const float* Rs; const float* Advs;
+  float* sv_dlv; float* loss_part;
+  float loss_scale, v_coef, e_coef;
+};
+
+__global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant__ nmarl_model m, const __grid_constant__ HeadFwdK k) {
+  __shared__ float red[3][4];
+  const int i = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x, B = k.B;
+  const nmarl_agent& ag = m.agent[i];
+  const int n_a = m.n_a;
+  const float* __restrict__ P = k.params;
+  float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+  if (b < B) {
+    const size_t row = (size_t)i * B + b;
+    float logit[NMARL_MAX_NA];
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
+    float v = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < NH / 4; ++q) {
+      const float4 h4 = *reinterpret_cast<const float4*>(k.h1 + row * NH + 4 * q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hv = f4get(h4, j);
+        const int u = 4 * q + j;
+#pragma unroll
+        for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+          if (cc < n_a) logit[cc] = fmaf(hv, __ldg(P + ag.o_pi_w + u * n_a + cc), logit[cc]);
+        v = fmaf(hv, __ldg(P + ag.o_v_w + u), v);
+      }
+    }
+    float pi[NMARL_MAX_NA];
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+      if (cc < n_a) { logit[cc] += __ldg(P + ag.o_pi_b + cc); mx = fmaxf(mx, logit[cc]); }
+    float se = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+      if (cc < n_a) { pi[cc] = expf(logit[cc] - mx); se += pi[cc]; } else pi[cc] = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) pi[cc] = pi[cc] / se;
+    for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + k.act[(size_t)ag.nbr[s] * B + b]);
+    v += __ldg(P + ag.o_v_b);
+    const int act = k.act[row];
+    const float R = k.Rs[row], Adv = k.Advs[row], cs = k.loss_scale;
+    float g[NMARL_MAX_NA];
+    float ent = 0.f, dot = 0.f, lpa = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < NMARL_MAX_NA; ++cc) {
+      g[cc] = 0.f;
+      if (cc < n_a) {
+        const float pc = fminf(fmaxf(pi[cc], 1e-10f), 1.0f);
+        const float in_rng = (pi[cc] >= 1e-10f && pi[cc] <= 1.0f) ? 1.0f : 0.0f;
+        const float lp = logf(pc);
+        ent -= pi[cc] * lp;
+        g[cc] = k.e_coef * cs * (lp + in_rng);
+        if (cc == act) { g[cc] += -cs * Adv * in_rng / pc; lpa = lp; }
+        dot += pi[cc] * g[cc];
+      }
+    }
+    float dl[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) dl[cc] = (cc < n_a) ? pi[cc] * (g[cc] - dot) : 0.f;
+    const float dvv = -k.v_coef * cs * (R - v);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dl[cc] = dvv;
+    *reinterpret_cast<float4*>(k.sv_dlv + row * 8) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+    *reinterpret_cast<float4*>(k.sv_dlv + row * 8 + 4) = make_float4(dl[4], dl[5], dl[6], dl[7]);
+    l_pol = -lpa * Adv; l_val = (R - v) * (R - v); l_ent = ent;
+  }
+  float vals[3] = {l_pol, l_val, l_ent};
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) {
+    float x = vals[cc];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[cc][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const float s = ((red[threadIdx.x][0] + red[threadIdx.x][1]) + red[threadIdx.x][2]) + red[threadIdx.x][3];
+    float* lp = k.loss_part + ((size_t)i * k.loss_tiles + 2 * blockIdx.x) * 4;
+    lp[threadIdx.x] = s;
+    if (2 * blockIdx.x + 1 < k.loss_tiles) lp[4 + threadIdx.x] = 0.f;
+  }
+}
+
 constexpr int BWD_BM = 64, BWD_TY = 16;
 
 template <int VAR>
@@ -728,6 +819,25 @@ extern "C" int nmarl_a2c_train_forward(const nmarl_model* m, const nmarl_bwd_arg
                                     a->v_coef, a->e_coef, st);
     if (rc) return rc;
   }
+  return 0;
+}
+
+extern "C" int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args* a, void* stream) {
+  if (check_bwd_args(m, a)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = m->n_agent, B = a->B, T = a->T;
+  const size_t nb = (size_t)N * B;
+  const int tiles = nmarl_fwd_tiles(B);
+  for (int t = 0; t < T; ++t) {
+    HeadFwdK k{};
+    k.B = B; k.loss_tiles = tiles; k.params = a->params;
+    k.h1 = a->h_seq + (size_t)(t + 1) * nb * NH;
+    k.act = a->act + (size_t)t * nb; k.Rs = a->Rs + (size_t)t * nb; k.Advs = a->Advs + (size_t)t * nb;
+    k.sv_dlv = a->sv_dlv + (size_t)t * nb * 8; k.loss_part = a->loss_part + (size_t)t * N * tiles * 4;
+    k.loss_scale = 1.0f / ((float)T * (float)a->B_total); k.v_coef = a->v_coef; k.e_coef = a->e_coef;
+    train_heads_kernel<<<dim3((B + 127) / 128, N), 128, 0, st>>>(*m, k);
+  }
+  NMARL_LAUNCH_CHECK();
   return 0;
 }
 

@@ -137,6 +137,9 @@ typedef struct {
   const float* wpack;      /* packed 3xTF32 operands (nmarl_pack_weights) or NULL.  When set and  */
                            /* B % 128 == 0 the tcgen05 tensor-core kernel is used, else FP32 FFMA */
   int32_t* tc_err;         /* device int: tensor-core pipeline watchdog (0 = ok); may be NULL      */
+  /* optional (p-call, tensor-core path only): save the activations BPTT needs while rolling out, so the
+   * update can skip the separate training forward (same inputs, same weights => same numbers):         */
+  float* sv_xin; float* sv_sh; float* sv_gates; float* sv_enc;   /* step-t slices, see nmarl_bwd_args      */
 } nmarl_fwd_args;
 
 int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
@@ -206,6 +209,9 @@ int nmarl_a2c_backward(const nmarl_model* m, const nmarl_bwd_args* a, void* stre
  * head gradients) and the reverse pass + weight gradients */
 int nmarl_a2c_train_forward(const nmarl_model* m, const nmarl_bwd_args* a, void* stream);
 int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, void* stream);
+/* when the rollout p-calls already saved the activations (nmarl_fwd_args.sv_*): only the heads, the loss
+ * partials and d(loss)/d(logits, v) are computed from h_seq -- replaces nmarl_a2c_train_forward             */
+int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args* a, void* stream);
 
 /* ---- K10: global-norm clip + TF-semantics RMSProp -------------------------------------------
  * Replaces tf.clip_by_global_norm + tf.train.RMSPropOptimizer (agents/policies.py:34-39,

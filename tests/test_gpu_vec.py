@@ -113,3 +113,30 @@ def test_auto_reset_of_finished_envs():
             assert torch.all(model.engine.h[model.engine.cur][:, torch.as_tensor(fresh).cuda()] == 0)
     assert seen_reset                      # random policies collide early in some envs
     assert np.isfinite(model.engine.params.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize('agent', ['ma2c_nc', 'ma2c_dial'])
+def test_saved_rollout_equals_separate_training_forward(agent):
+    """Tensor-core path: activations saved by the rollout p-calls + the heads-only kernel give the same
+    gradient as the reference-style separate training forward (same inputs and weights)."""
+    grads = []
+    for fuse in (True, False):
+        cp, env, model, vt = _make(agent, 128, sample='uniform')
+        e = model.engine
+        assert e.use_tc
+        e.fuse_save = fuse
+        rs = np.random.RandomState(0)
+        env.reset_device(u01=torch.as_tensor(rs.rand(1, 128)).to(env.device))
+        e.reset_states(); e.begin_episode(env)
+        uni = torch.as_tensor(rs.rand(e.T + 1, e.N, 128)).to(env.device)
+        for _ in range(2):                      # second batch starts from a non-zero LSTM state
+            e.rollout(env, sample='uniform', uniforms=uni)
+            assert e.saved_rollout == fuse
+            e.compute_returns(); e.backward(); e.apply(5e-4); e.roll_buffers()
+        e.check_tc()
+        torch.cuda.synchronize()
+        grads.append((e.grads.clone(), e.params.clone(), e.act_buf.clone(), torch.tensor(e.losses()['policy_loss'])))
+    assert torch.equal(grads[0][2], grads[1][2])
+    torch.testing.assert_close(grads[0][0], grads[1][0], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(grads[0][1], grads[1][1], rtol=0, atol=1e-6)
+    torch.testing.assert_close(grads[0][3], grads[1][3], rtol=1e-5, atol=1e-7)
