@@ -12,7 +12,9 @@ struct FwdK {
   float* loss_part;                      // [N][loss_tiles][4]
   int loss_tiles;                        // entries per agent in loss_part (64-row tiles)
   float loss_scale, v_coef, e_coef;
+  long long* prof;                       // debug: per-phase clock64 stamps of CTA (0,0) or NULL
 };
+extern long long* g_nmarl_prof;          // set by nmarl_debug_set_prof
 
 // tcgen05 path (tc_cell.cu): returns 0 on success
 int nmarl_tc_launch_fwd(const nmarl_model* m, const FwdK& k, int mode, cudaStream_t st);

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float tcv = tanhf(f4get(cc, j));
+          const float tcv = ftanh(f4get(cc, j));
           dct[4 * q + j] += dh[4 * q + j] * f4get(go, j) * (1.0f - tcv * tcv);
         }
       }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float og = f4get(go, j), tcv = tanhf(f4get(cc, j));
+            const float og = f4get(go, j), tcv = ftanh(f4get(cc, j));
             dz[4 * q + j] = dh[4 * q + j] * tcv * og * (1.0f - og);
           }
         }

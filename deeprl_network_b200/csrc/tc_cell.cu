@@ -59,39 +59,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
-    // ---- k-block schedule shared by the three roles --------------------------------------------------
+    // ---- k-block schedule shared by the three roles: all encoder GEMMs first (each into its own 64-column
+    // block of the accumulator region, one completion barrier), then the gate GEMM over [s | h^] ----------------
     int n = 0;
-    auto add = [&](int off_floats, int N, int K, int kb, int first, int last_enc, int last_acc) {
-      sched[n++] = make_kb(off_floats, N, K, kb, N == 64, first, last_enc, last_acc);
-    };
-    const int KG = SD + NH;                                    // gate GEMM depth
-    const int nG = KG / 32;
-    int g = 0;
-    auto gate2 = [&]() { for (int j = 0; j < 2; ++j, ++g) add(ag.tp_g, 256, KG, g, g == 0, 0, g == nG - 1); };
-    add(ag.tp_x, 64, Kx, 0, 1, 1, 0);                          // X (Kx <= 32 on this path)
-    if (VAR == NMARL_NC) {
-      gate2();
-      add(ag.tp_p, 64, ag.n_nbr * n_a, 0, 1, 1, 0);
-      gate2();
-      const int nM = 2 * ag.n_nbr;
-      for (int j = 0; j < nM; ++j) add(ag.tp_m, 64, NH * ag.n_nbr, j, j == 0, j == nM - 1, 0);
-      gate2();
-      gate2();
-    } else if (VAR == NMARL_IA2C) {
-      gate2();
-      gate2();
-    } else if (VAR == NMARL_IC3) {
-      for (int j = 0; j < 2; ++j) add(ag.tp_m, 64, NH, j, j == 0, j == 1, 0);
-      gate2();
-      gate2();
-    } else {
-      const int nM = 2 * ag.n_nbr;
-      for (int j = 0; j < nM; ++j) add(ag.tp_m, 64, NH * ag.n_nbr, j, j == 0, j == nM - 1, 0);
-      gate2();
-      gate2();
-      if (MODE != MODE_V)
-        for (int j = 0; j < 2; ++j) add(ag.tp_mfc, 64, NH, j, j == 0, j == 1, 0);
+    const int KG = SD + NH, nG = KG / 32;
+    sched[n++] = make_kb(ag.tp_x, 64, Kx, 0, ACC_COL, 1, VAR == NMARL_IA2C, 0);          // X (Kx <= 32 on this path)
+    if (VAR == NMARL_NC) sched[n++] = make_kb(ag.tp_p, 64, ag.n_nbr * n_a, 0, ACC_COL + 64, 1, 0, 0);
+    if (VAR != NMARL_IA2C) {
+      const int nM = (VAR == NMARL_IC3) ? 2 : 2 * ag.n_nbr;
+      const int KM = (VAR == NMARL_IC3) ? NH : NH * ag.n_nbr;
+      const int mcol = (VAR == NMARL_NC) ? ACC_COL + 128 : ACC_COL + 64;
+      for (int j = 0; j < nM; ++j) sched[n++] = make_kb(ag.tp_m, 64, KM, j, mcol, j == 0, j == nM - 1, 0);
     }
+    for (int g = 0; g < nG; ++g) sched[n++] = make_kb(ag.tp_g, 256, KG, g, ACC_COL, g == 0, 0, g == nG - 1);
+    if (VAR == NMARL_DIAL && MODE != MODE_V)
+      for (int j = 0; j < 2; ++j) sched[n++] = make_kb(ag.tp_mfc, 64, NH, j, ACC_COL, j == 0, j == 1, 0);
     *n_kb_s = n;
   }
   if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
@@ -113,148 +95,181 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     const int LDI = m.kx_pad + m.kp_pad + m.km_pad;
     float* xin_row = SAVE ? k.sv_xin + row * LDI : nullptr;
     float* sh_row = SAVE ? k.sv_sh + row * (SD + NH) : nullptr;
+    long long* prof = (k.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1 && tid == 0) ? k.prof : nullptr;
+    int pi_ = 0;
+#define STAMP() do { if (prof) prof[pi_++] = clock64(); } while (0)
+    STAMP();
     const int c0 = set * W;             // this thread's columns inside every 32-wide input k-block
     const int e0 = set * EW;            // this thread's hidden units / encoder columns
 
-    // ---- X encoder input: own + neighbours' observation rows --------------------------------------------
-    {
-      float xv[W];
+    // ---- gather every encoder input of this thread up front (all loads in flight together) ------------------
+    float xv[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const int kk = c0 + j;
+      float val = 0.f;
+      if (kk < Kx) {
+        const int s = kk / ag.x_w, f = kk - s * ag.x_w;
+        val = a.obs[((size_t)ag.x_src[s] * B + b) * m.obs_stride + f];
+      }
+      xv[j] = val;
+    }
+    float pv[W];
+    if (VAR == NMARL_NC) {
+      const int Kp = ag.n_nbr * n_a;
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const int kk = c0 + j;
         float val = 0.f;
-        if (kk < Kx) {
-          const int s = kk / ag.x_w, f = kk - s * ag.x_w;
-          val = a.obs[((size_t)ag.x_src[s] * B + b) * m.obs_stride + f];
+        if (kk < Kp) {
+          const int s = kk / n_a, f = kk - s * n_a;
+          val = a.fp[((size_t)ag.nbr[s] * B + b) * n_a + f];
         }
-        xv[j] = val;
+        pv[j] = val;
       }
-      if (SAVE && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
-      produce_in(c, xv);
     }
-    float s0[EW];                       // this thread's slice of the encoder output being assembled
-    enc_load(c, s0);
-    bias_act(s0, P + ag.o_b_ob + e0, VAR == NMARL_IC3 ? 1 : 0);
-    if (SAVE && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
-
-    if (VAR == NMARL_NC) {
-      if (SAVE) store_vec<EW>(sh_row + e0, s0);
-      produce_act(c, s0);
-      // ---- fingerprint encoder ----
-      {
-        float pv[W];
-        const int Kp = ag.n_nbr * n_a;
+    constexpr int NPRE = 2;                      // neighbours whose messages are prefetched into registers
+    float mv[NPRE][2][W];
+    if (VAR == NMARL_NC || VAR == NMARL_DIAL) {
+      const float* src = (VAR == NMARL_NC) ? a.h_in : a.msg_in;          // messages: UN-masked (utils.py:182-183)
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          const int kk = c0 + j;
-          float val = 0.f;
-          if (kk < Kp) {
-            const int s = kk / n_a, f = kk - s * n_a;
-            val = a.fp[((size_t)ag.nbr[s] * B + b) * n_a + f];
-          }
-          pv[j] = val;
-        }
-        if (SAVE && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
-        produce_in(c, pv);
-      }
-      enc_load(c, s0);
-      bias_act(s0, P + ag.o_b_fp + e0, 0);
-      if (SAVE) store_vec<EW>(sh_row + NH + e0, s0);
-      produce_act(c, s0);
-    }
-    if (VAR != NMARL_IA2C) {
-      // ---- message encoder: neighbours' UN-masked h (NC), their mean (IC3) or their messages (DIAL) ----
-      float* xm = SAVE ? xin_row + m.kx_pad + m.kp_pad : nullptr;
-      if (VAR == NMARL_IC3) {
-        const float nn = (float)ag.n_nbr;
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          float mv[W];
-#pragma unroll
-          for (int j = 0; j < W; ++j) mv[j] = 0.f;
-          for (int s = 0; s < ag.n_nbr; ++s) {
-            const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
-#pragma unroll
-            for (int q = 0; q < W / 4; ++q) {
-              const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
-              mv[4 * q] += w.x; mv[4 * q + 1] += w.y; mv[4 * q + 2] += w.z; mv[4 * q + 3] += w.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < W; ++j) mv[j] /= nn;
-          if (SAVE) store_vec<W>(xm + hb * 32 + c0, mv);
-          produce_in(c, mv);
-        }
-      } else {
-        const float* src = (VAR == NMARL_NC) ? a.h_in : a.msg_in;
-        for (int s = 0; s < ag.n_nbr; ++s) {
+      for (int s = 0; s < NPRE; ++s) {
+        if (s < ag.n_nbr) {
           const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH + c0;
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {
-            float mv[W];
+          for (int hb = 0; hb < 2; ++hb)
 #pragma unroll
             for (int q = 0; q < W / 4; ++q) {
               const float4 w = *reinterpret_cast<const float4*>(hp + hb * 32 + 4 * q);
-              mv[4 * q] = w.x; mv[4 * q + 1] = w.y; mv[4 * q + 2] = w.z; mv[4 * q + 3] = w.w;
+              mv[s][hb][4 * q] = w.x; mv[s][hb][4 * q + 1] = w.y; mv[s][hb][4 * q + 2] = w.z; mv[s][hb][4 * q + 3] = w.w;
             }
-            if (SAVE) store_vec<W>(xm + s * NH + hb * 32 + c0, mv);
-            produce_in(c, mv);
-          }
-        }
-        if (SAVE) {
-          float z[W];
-#pragma unroll
-          for (int j = 0; j < W; ++j) z[j] = 0.f;
-          for (int q = ag.n_nbr * 2; q < m.km_pad / 32; ++q) store_vec<W>(xm + q * 32 + c0, z);
         }
       }
+    }
+    if (VAR == NMARL_IC3) {                                               // mean of the neighbours' h (utils.py:395)
+      const float nn = (float)ag.n_nbr;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) mv[0][hb][j] = 0.f;
+        for (int s = 0; s < ag.n_nbr; ++s) {
+          const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
+#pragma unroll
+          for (int q = 0; q < W / 4; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
+            mv[0][hb][4 * q] += w.x; mv[0][hb][4 * q + 1] += w.y; mv[0][hb][4 * q + 2] += w.z; mv[0][hb][4 * q + 3] += w.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) mv[0][hb][j] /= nn;
+      }
+    }
+    float hv[2][W];                                                       // own h, done-masked (utils.py:189-190)
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+      const float* hp = a.h_in + row * NH + hb * 32 + c0;
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
+        hv[hb][4 * q] = w.x * nd; hv[hb][4 * q + 1] = w.y * nd; hv[hb][4 * q + 2] = w.z * nd; hv[hb][4 * q + 3] = w.w * nd;
+      }
+    }
+    STAMP();
+    // ---- encoder GEMMs: A chunks back to back, one completion wait ----------------------------------------------
+    float* xm = SAVE ? xin_row + m.kx_pad + m.kp_pad : nullptr;
+    if (SAVE && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
+    produce_in(c, xv);
+    if (VAR == NMARL_NC) {
+      if (SAVE && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
+      produce_in(c, pv);
+    }
+    if (VAR == NMARL_IC3) {
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        if (SAVE) store_vec<W>(xm + hb * 32 + c0, mv[0][hb]);
+        produce_in(c, mv[0][hb]);
+      }
+    } else if (VAR != NMARL_IA2C) {
+      const float* src = (VAR == NMARL_NC) ? a.h_in : a.msg_in;
+      for (int s = 0; s < ag.n_nbr; ++s) {
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          float t[W];
+          if (s < NPRE) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) t[j] = (s == 0) ? mv[0][hb][j] : mv[NPRE - 1][hb][j];
+          } else {
+            const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
+#pragma unroll
+            for (int q = 0; q < W / 4; ++q) {
+              const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
+              t[4 * q] = w.x; t[4 * q + 1] = w.y; t[4 * q + 2] = w.z; t[4 * q + 3] = w.w;
+            }
+          }
+          if (SAVE) store_vec<W>(xm + s * NH + hb * 32 + c0, t);
+          produce_in(c, t);
+        }
+      }
+      if (SAVE) {
+        float z[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) z[j] = 0.f;
+        for (int q = ag.n_nbr * 2; q < m.km_pad / 32; ++q) store_vec<W>(xm + q * 32 + c0, z);
+      }
+    }
+    STAMP();
+    enc_wait(c);
+    STAMP();
+    // ---- encoder epilogues -> s, fed to the gate GEMM ---------------------------------------------------------------
+    float s0[EW];
+    enc_load(c, ACC_COL, s0);
+    bias_act(s0, P + ag.o_b_ob + e0, VAR == NMARL_IC3 ? 1 : 0);
+    if (SAVE && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
+    if (VAR == NMARL_NC) {
+      float s1[EW], s2[EW];
+      enc_load(c, ACC_COL + 64, s1);
+      enc_load(c, ACC_COL + 128, s2);
+      bias_act(s1, P + ag.o_b_fp + e0, 0);
+      bias_act(s2, P + ag.o_b_msg + e0, 0);
+      if (SAVE) { store_vec<EW>(sh_row + e0, s0); store_vec<EW>(sh_row + NH + e0, s1); store_vec<EW>(sh_row + 2 * NH + e0, s2); }
+      produce_act(c, s0);
+      produce_act(c, s1);
+      produce_act(c, s2);
+    } else if (VAR == NMARL_IA2C) {
+      if (SAVE) store_vec<EW>(sh_row + e0, s0);
+      produce_act(c, s0);
+    } else {
       float s1[EW];
-      enc_load(c, s1);
-      if (VAR == NMARL_NC) {
-        bias_act(s1, P + ag.o_b_msg + e0, 0);
-        if (SAVE) store_vec<EW>(sh_row + 2 * NH + e0, s1);
-        produce_act(c, s1);
-      } else if (VAR == NMARL_IC3) {
+      enc_load(c, ACC_COL + 64, s1);
+      if (VAR == NMARL_IC3) {                                            // s = tanh(..) + m W_msg + b  (utils.py:400)
         bias_act(s1, P + ag.o_b_msg + e0, 2);
 #pragma unroll
         for (int j = 0; j < EW; ++j) s0[j] += s1[j];
-        if (SAVE) store_vec<EW>(sh_row + e0, s0);
-        produce_act(c, s0);
-      } else {  // DIAL
+      } else {                                                           // DIAL: relu + relu + onehot(argmax p_i)
         bias_act(s1, P + ag.o_b_msg + e0, 0);
         if (SAVE) store_vec<EW>(k.sv_enc + row * 128 + NH + e0, s1);
         int am = 0;
         {
           const float* pr = a.fp + row * n_a;
           float best = pr[0];
-          for (int cc = 1; cc < n_a; ++cc) { const float pv = pr[cc]; if (pv > best) { best = pv; am = cc; } }
+          for (int cc = 1; cc < n_a; ++cc) { const float pvv = pr[cc]; if (pvv > best) { best = pvv; am = cc; } }
         }
 #pragma unroll
         for (int j = 0; j < EW; ++j) s0[j] = (s0[j] + s1[j]) + ((e0 + j) == am ? 1.0f : 0.0f);
-        if (SAVE) store_vec<EW>(sh_row + e0, s0);
-        produce_act(c, s0);
       }
-    } else {
       if (SAVE) store_vec<EW>(sh_row + e0, s0);
       produce_act(c, s0);
     }
-    // ---- own h (done-masked): two input k-blocks --------------------------------------------------------------
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-      float hv[W];
-      const float* hp = a.h_in + row * NH + hb * 32 + c0;
-#pragma unroll
-      for (int q = 0; q < W / 4; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
-        hv[4 * q] = w.x * nd; hv[4 * q + 1] = w.y * nd; hv[4 * q + 2] = w.z * nd; hv[4 * q + 3] = w.w * nd;
-      }
-      if (SAVE) store_vec<W>(sh_row + SD + hb * 32 + c0, hv);
-      produce_in(c, hv);
+      if (SAVE) store_vec<W>(sh_row + SD + hb * 32 + c0, hv[hb]);
+      produce_in(c, hv[hb]);
     }
-
+    STAMP();
     // ---- LSTM cell update for hidden units [e0, e0 + EW), 8 at a time; partial head sums -----------------------
     tc::mbar_wait(acc_full, 0, a.tc_err, 13);
     tc::fence_after_sync();
+    STAMP();
     float logit[NMARL_MAX_NA];
 #pragma unroll
     for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
@@ -267,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 2 * NH + u0, go);
       tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 3 * NH + u0, gu);
       tc::wait_ld();
+      STAMP();
       float cn[8], hn[8];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -278,14 +294,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int x = 4 * q + j;
-          gi[x] = sigmoidf_(gi[x] + f4get(bi, j));
-          gf[x] = sigmoidf_(gf[x] + f4get(bf, j));
-          go[x] = sigmoidf_(go[x] + f4get(bo, j));
-          gu[x] = tanhf(gu[x] + f4get(bu, j));
+          gi[x] = fsigmoid(gi[x] + f4get(bi, j));
+          gf[x] = fsigmoid(gf[x] + f4get(bf, j));
+          go[x] = fsigmoid(go[x] + f4get(bo, j));
+          gu[x] = ftanh(gu[x] + f4get(bu, j));
           cn[x] = gf[x] * (f4get(cp4, j) * nd) + gi[x] * gu[x];
-          hn[x] = go[x] * tanhf(cn[x]);
+          hn[x] = go[x] * ftanh(cn[x]);
         }
       }
+      STAMP();
       if (MODE != MODE_V) {
         store_vec<8>(a.c_out + row * NH + u0, cn);
         store_vec<8>(a.h_out + row * NH + u0, hn);
@@ -294,17 +311,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         float* gs = k.sv_gates + row * NG + u0;
         store_vec<8>(gs + 0 * NH, gi); store_vec<8>(gs + 1 * NH, gf); store_vec<8>(gs + 2 * NH, go); store_vec<8>(gs + 3 * NH, gu);
       }
+      STAMP();
       if (MODE != MODE_V) {
+        if (n_a == 4) {
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
+          for (int x = 0; x < 8; ++x) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(P + ag.o_pi_w) + u0 + x);
+            logit[0] = fmaf(hn[x], w4.x, logit[0]); logit[1] = fmaf(hn[x], w4.y, logit[1]);
+            logit[2] = fmaf(hn[x], w4.z, logit[2]); logit[3] = fmaf(hn[x], w4.w, logit[3]);
+          }
+        } else {
 #pragma unroll
-          for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
-            if (cc < n_a) logit[cc] = fmaf(hn[x], __ldg(P + ag.o_pi_w + (u0 + x) * n_a + cc), logit[cc]);
+          for (int x = 0; x < 8; ++x)
+#pragma unroll
+            for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+              if (cc < n_a) logit[cc] = fmaf(hn[x], __ldg(P + ag.o_pi_w + (u0 + x) * n_a + cc), logit[cc]);
+        }
       }
       if (!SAMPLE) {
-#pragma unroll
-        for (int x = 0; x < 8; ++x) v = fmaf(hn[x], __ldg(P + ag.o_v_w + u0 + x), v);
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(P + ag.o_v_w + u0)), v1 = __ldg(reinterpret_cast<const float4*>(P + ag.o_v_w + u0) + 1);
+        v = fmaf(hn[0], v0.x, v); v = fmaf(hn[1], v0.y, v); v = fmaf(hn[2], v0.z, v); v = fmaf(hn[3], v0.w, v);
+        v = fmaf(hn[4], v1.x, v); v = fmaf(hn[5], v1.y, v); v = fmaf(hn[6], v1.z, v); v = fmaf(hn[7], v1.w, v);
       }
+      STAMP();
       if (VAR == NMARL_DIAL && MODE != MODE_V) {          // stash h' for the sender-side message fc below
 #pragma unroll
         for (int x = 0; x < 8; ++x) s0[(u0 - e0) + x] = hn[x];
@@ -320,7 +349,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc) hp[cc] = logit[cc];
       hp[NMARL_MAX_NA - 1] = v;
     }
+    STAMP();
     row_barrier();
+    STAMP();
     float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
     if (set == 0) {
 #pragma unroll
@@ -404,10 +435,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     }
     if (VAR == NMARL_DIAL && MODE != MODE_V) {            // msg' = relu(h' W_mfc + b)   (utils.py:563-566)
       float mo[EW];
-      enc_load(c, mo);
+      enc_wait(c);
+      enc_load(c, ACC_COL, mo);
       bias_act(mo, P + ag.o_mfc_b + e0, 0);
       store_vec<EW>(a.msg_out + row * NH + e0, mo);
     }
+    STAMP();
+    if (prof) prof[31] = pi_;
     if (MODE == MODE_TRAIN && set == 0) {
       float vals[3] = {l_pol, l_val, l_ent};
 #pragma unroll
@@ -422,7 +456,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     if (lane == 0) producer_loop(sched, n_kb, bst, b_full, b_empty, a.wpack, a.tc_err);
   } else {
     // =================================== MMA issuer ======================================================
-    if (lane == 0) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, a.tc_err);
+    if (lane == 0) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, a.tc_err,
+                            (k.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1) ? k.prof : nullptr);
   }
   __syncthreads();
   if (MODE == MODE_TRAIN && tid < 3) {
@@ -444,7 +479,9 @@ int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(k.a.B / 128, m->n_agent);
-  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k);
+  FwdK k2 = k;
+  k2.prof = g_nmarl_prof;
+  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k2);
   NMARL_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@ namespace tcrow {
 
 constexpr int S_STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 2 * 256 * 128;          // hi+lo tiles of the widest operand (N = 256)
-constexpr uint32_t ACC_COL = 0, ENC_COL = 256, A_COL = 320;
+constexpr uint32_t ACC_COL = 0, A_COL = 256;            // TMEM: [0,256) accumulators (encoders reuse it), [256,384) A ring
 constexpr int MAX_KB = 40;
 // NSET warp-sets share every env row: set s of row r works on columns [s*W, (s+1)*W) of each 32-wide input
 // k-block and on hidden units [s*EW, (s+1)*EW) of the encoders / LSTM cell.  4 sets = 16 row warps per SM
@@ -22,7 +22,8 @@ static_assert(W % 8 == 0 && EW % 8 == 0, "8-column TMEM pieces");
 
 struct KbEnt {
   uint32_t off_bytes, bytes;
-  uint8_t ksteps, n64, first, last_enc, last_acc, pad0, pad1, pad2;
+  uint16_t dcol;                                          // accumulator column of this GEMM
+  uint8_t ksteps, first, last_enc, last_acc, pad0, pad1;
 };
 
 struct RowCtx {
@@ -77,15 +78,18 @@ __device__ __forceinline__ void produce_act(RowCtx& c, const float (&s)[EW]) {
     produce_end(c);
   }
 }
-// this thread's EW columns of the encoder accumulator
-__device__ __forceinline__ void enc_load(RowCtx& c, float (&v)[EW]) {
+// wait for the encoder GEMMs issued so far
+__device__ __forceinline__ void enc_wait(RowCtx& c) {
   tc::mbar_wait(c.enc_full, c.e & 1, c.err, 12);
   c.e++;
   tc::fence_after_sync();
+}
+// this thread's EW columns of a 64-wide result block at accumulator column `col`
+__device__ __forceinline__ void enc_load(RowCtx& c, uint32_t col, float (&v)[EW]) {
 #pragma unroll
   for (int p = 0; p < EW / 8; ++p) {
     float t[8];
-    tc::tmem_ld8(c.tmem + c.lane_base + ENC_COL + c.set * EW + 8 * p, t);
+    tc::tmem_ld8(c.tmem + c.lane_base + col + c.set * EW + 8 * p, t);
     tc::wait_ld();
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[8 * p + j] = t[j];
@@ -106,6 +110,10 @@ __device__ __forceinline__ void bias_act(float (&v)[EW], const float* __restrict
     for (int j = 0; j < 4; ++j) v[4 * q + j] = act == 0 ? fmaxf(z[j], 0.f) : (act == 1 ? tanhf(z[j]) : z[j]);
   }
 }
+// MUFU-based activations for the tensor-core epilogues (ex2.approx + rcp): absolute error ~1e-7, well inside the
+// 1e-5 parity budget, ~6x fewer instructions than expf/tanhf + IEEE division.
+__device__ __forceinline__ float fsigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return fmaf(2.0f, __frcp_rn(1.0f + __expf(-2.0f * x)), -1.0f); }
 __device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
 
 
@@ -123,18 +131,20 @@ __device__ __forceinline__ void producer_loop(const KbEnt* sched, int n_kb, uint
 }
 __device__ __forceinline__ void mma_loop(const KbEnt* sched, int n_kb, uint8_t* bst, uint64_t* b_full, uint64_t* b_empty,
                                          uint64_t* a_full, uint64_t* a_empty, uint64_t* enc_full, uint64_t* acc_full,
-                                         uint32_t tmem, int* err) {
+                                         uint32_t tmem, int* err, long long* prof = nullptr) {
   for (int q = 0; q < n_kb; ++q) {
     const int st = q % S_STAGES, slot = q & 1;
     const KbEnt e = sched[q];
     tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, err, 31);
+    if (prof) prof[32 + 3 * q] = clock64();
     tc::mbar_wait(&a_full[slot], (q >> 1) & 1, err, 32);
     tc::fence_after_sync();
+    if (prof) prof[33 + 3 * q] = clock64();
     const uint32_t tile = e.bytes / 2;
     const uint32_t ncols = tile / 128;                       // N of this operand
     const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile);
     const uint32_t idesc = tc::idesc_tf32(128, ncols);
-    const uint32_t dcol = tmem + (e.n64 ? ENC_COL : ACC_COL);
+    const uint32_t dcol = tmem + e.dcol;
     for (int ks = 0; ks < e.ksteps; ++ks) {
       const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
       tc::mma_tf32_ts(dcol, a_hi, d_hi + 2 * ks, idesc, (e.first && ks == 0) ? 0u : 1u);
@@ -145,16 +155,17 @@ __device__ __forceinline__ void mma_loop(const KbEnt* sched, int n_kb, uint8_t* 
     tc::mma_commit(&b_empty[st]);
     if (e.last_enc) tc::mma_commit(enc_full);
     if (e.last_acc) tc::mma_commit(acc_full);
+    if (prof) prof[34 + 3 * q] = clock64();
   }
 }
-__device__ __forceinline__ KbEnt make_kb(int off_floats, int N, int K, int kb, int to_enc, int first, int last_enc, int last_acc) {
+__device__ __forceinline__ KbEnt make_kb(int off_floats, int N, int K, int kb, int dcol, int first, int last_enc, int last_acc) {
   KbEnt e;
   e.off_bytes = (uint32_t)(off_floats + kb * 2 * N * 32) * 4u;
   e.bytes = 2u * N * 128u;
   const int k8 = (K + 7) / 8 * 8;
   e.ksteps = (uint8_t)min(4, (k8 - kb * 32) / 8);
-  e.n64 = to_enc; e.first = first; e.last_enc = last_enc; e.last_acc = last_acc;
-  e.pad0 = e.pad1 = e.pad2 = 0;
+  e.dcol = (uint16_t)dcol; e.first = first; e.last_enc = last_enc; e.last_acc = last_acc;
+  e.pad0 = e.pad1 = 0;
   return e;
 }
 constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 16 * 8 + 16 + MAX_KB * sizeof(KbEnt) + NSET * 128 * 8 * sizeof(float);

@@ -61,9 +61,9 @@ def test_tensor_core_cell_matches_ffma_cell(variant):
         e.step_v(obs_dev(lay, base), nb(fp), to_dev(done), act, v)
         e.check_tc()
         outs.append((pi, act, v, e.get_states_fw().clone(), None if e.msg[e.cur] is None else e.msg[e.cur].clone()))
-    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=2e-6)
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=4e-6)
     torch.testing.assert_close(outs[0][2], outs[1][2], rtol=0, atol=5e-6)
-    torch.testing.assert_close(outs[0][3], outs[1][3], rtol=0, atol=2e-6)
+    torch.testing.assert_close(outs[0][3], outs[1][3], rtol=0, atol=4e-6)
     assert (outs[0][1] != outs[1][1]).float().mean().item() < 0.002          # only at cdf boundaries
     if outs[0][4] is not None:
-        torch.testing.assert_close(outs[0][4], outs[1][4], rtol=0, atol=2e-6)
+        torch.testing.assert_close(outs[0][4], outs[1][4], rtol=0, atol=4e-6)
