@@ -67,7 +67,7 @@ class BwdArgs(C.Structure):
                 ('dh_rec', C.c_void_p), ('dc_rec', C.c_void_p), ('dmsg', C.c_void_p),
                 ('wt', C.c_void_p), ('ws', C.c_void_p), ('ws_floats', C.c_int64),
                 ('loss_part', C.c_void_p), ('grads', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
-                ('sv_dzT', C.c_void_p)]
+                ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p)]
 
 
 _lib = None

@@ -282,7 +282,10 @@ class PolicyEngine:
         self.sv_dlv = z(T, N, B, 8)
         self.sv_dz = z(T, N, B, 4 * NH)
         self.sv_dpre = z(T, N, B, 192)
-        self.sv_dzT = z(T, N, B // 32, 2 * 256 * 32) if (self.use_tc and lay.s_dim + NH == 256) else None
+        # tensor-core path: dz / encoder pre-activation gradients additionally as K-major [hi | lo] operand tiles
+        ndp = {'ma2c_nc': 192, 'ia2c': 64}.get(self.variant, 128)
+        self.sv_dzT = z(T, N, B // 32, 2 * 256 * 32) if self.use_tc else None
+        self.sv_dpT = z(T, N, B // 32, 2 * ndp * 32) if self.use_tc else None
         self.sv_dmp = z(T, N, B, NH) if self.variant == 'ma2c_dial' else None
         self.dh_rec, self.dc_rec = z(2, N, B, NH), z(2, N, B, NH)
         self.dmsg = z(2, N, L.MAX_NBR, B, NH) if self.variant != 'ia2c' else None
@@ -307,7 +310,7 @@ class PolicyEngine:
         a.wt, a.ws, a.ws_floats = L.ptr(self.wt), L.ptr(self.ws), self.ws_floats
         a.loss_part, a.grads = L.ptr(self.loss_part), L.ptr(self.grads)
         a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
-        a.sv_dzT = L.ptr(self.sv_dzT)
+        a.sv_dzT, a.sv_dpT = L.ptr(self.sv_dzT), L.ptr(self.sv_dpT)
         return a
 
     def backward(self):

@@ -14,11 +14,14 @@ struct BwdK {
   float* sv_dz; float* sv_dpre;                                        // step t
   const float* wpack; int* tc_err;                                     // tcgen05 path (NULL -> FFMA)
   float* dzT;                                                          // step t: [N][B/32][hi|lo][256][32] tiles or NULL
+  float* dpT;                                                          // step t: [N][B/32][hi|lo][ndp][32] tiles (encoder pre-act grads)
+  int ndp;                                                             // rows of a dpT tile: 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C)
 };
 
 int nmarl_tc_launch_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st);
 int nmarl_tc_wgrad_splits(int n_agent);
 int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m);
-int nmarl_tc_launch_gate_wgrad(const nmarl_model* m, int B, int T, const float* sv_sh, const float* dzT, const float* sv_dz,
-                               float* ws, int* err, int* splits_out, cudaStream_t st);
-int nmarl_tc_launch_bias_reduce(const nmarl_model* m, const float* ws, int splits, float* grads, cudaStream_t st);
+int nmarl_tc_ndp(const nmarl_model* m);
+// all GEMM weight gradients (gate + encoders) of the tensor-core path; activations are feature-major
+int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st);

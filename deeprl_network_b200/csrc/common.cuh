@@ -36,6 +36,19 @@ void nmarl_set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
+// debug aid: NMARL_DEBUG_SYNC=1 synchronises and reports after each stage of the backward pass
+#include <stdlib.h>
+#define NMARL_DBG_SYNC(st, name)                                                            \
+  do {                                                                                      \
+    static int dbg_ = -1;                                                                   \
+    if (dbg_ < 0) dbg_ = (getenv("NMARL_DEBUG_SYNC") != nullptr);                           \
+    if (dbg_) {                                                                             \
+      fprintf(stderr, "[nmarl] %s ...", name); fflush(stderr);                              \
+      cudaError_t e2_ = cudaStreamSynchronize(st);                                          \
+      fprintf(stderr, " %s\n", cudaGetErrorString(e2_)); fflush(stderr);                    \
+    }                                                                                       \
+  } while (0)
+
 // ---- cp.async (LDGSTS) staging ------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -26,11 +26,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug must not hang the GPU.  On timeout *err is set and the wait returns.
+// Bounded wait: a protocol bug must not hang the GPU.  The deadline is in SM clock cycles (~70 ms); once any
+// wait of the grid has timed out (*err != 0) every later wait gives up immediately so the kernel drains.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+  const long long t0 = clock64();
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -39,8 +41,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return true;
+    if (clock64() - t0 > (1ll << 27)) break;
+    if (err != nullptr && *reinterpret_cast<volatile int*>(err) != 0) return false;
   }
-  if (err != nullptr) atomicExch(err, code);
+  if (err != nullptr) atomicCAS(err, 0, code);
   return false;
 }
 

@@ -60,7 +60,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
     const size_t row = (size_t)i * B + b;
     const float nd = 1.0f - k.done_pre[b];
     const int e0 = set * EW;                       // this thread's 16 hidden units
-    const float* gs = k.sv_gates + row * NG + e0;
+    // saved activations are feature-major on this path ([agent][feature][env])
+    const float* gates_fm = k.sv_gates + (size_t)i * NG * B;
+    const float* sh_fm = k.sv_sh + (size_t)i * (SD + NH) * B;
+    const float* enc_fm = k.sv_enc ? k.sv_enc + (size_t)i * 128 * B : nullptr;
+    float* dz_fm = k.sv_dz + (size_t)i * NG * B;
 
     // ---- total dh and dc for the thread's units --------------------------------------------------------------
     float dh[EW], dct[EW];
@@ -100,54 +104,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         }
       }
       // dc_t += dh * o * (1 - tanh(c_t)^2)
+      float gov[EW];
+      ld_fm<EW>(gates_fm, 2 * NH + e0, B, b, gov);
 #pragma unroll
       for (int q = 0; q < EW / 4; ++q) {
-        const float4 go = *reinterpret_cast<const float4*>(gs + 2 * NH + 4 * q);
         const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float tcv = ftanh(f4get(cc, j));
-          dct[4 * q + j] += dh[4 * q + j] * f4get(go, j) * (1.0f - tcv * tcv);
+          dct[4 * q + j] += dh[4 * q + j] * gov[4 * q + j] * (1.0f - tcv * tcv);
         }
       }
     }
     // ---- gate derivatives, gate by gate = k-block pair by k-block pair of the dgrad A operand -----------------
-    float* zo = k.sv_dz + row * NG + e0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float dz[EW];
+      if (g == 0 || g == 3) {
+        float gi[EW], gu[EW];
+        ld_fm<EW>(gates_fm, 0 * NH + e0, B, b, gi);
+        ld_fm<EW>(gates_fm, 3 * NH + e0, B, b, gu);
 #pragma unroll
-      for (int q = 0; q < EW / 4; ++q) {
-        if (g == 0 || g == 3) {
-          const float4 gi = *reinterpret_cast<const float4*>(gs + 0 * NH + 4 * q);
-          const float4 gu = *reinterpret_cast<const float4*>(gs + 3 * NH + 4 * q);
+        for (int j = 0; j < EW; ++j)
+          dz[j] = (g == 0) ? dct[j] * gu[j] * gi[j] * (1.0f - gi[j]) : dct[j] * gi[j] * (1.0f - gu[j] * gu[j]);
+      } else if (g == 1) {
+        float gf[EW];
+        ld_fm<EW>(gates_fm, 1 * NH + e0, B, b, gf);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float ig = f4get(gi, j), ug = f4get(gu, j);
-            dz[4 * q + j] = (g == 0) ? dct[4 * q + j] * ug * ig * (1.0f - ig) : dct[4 * q + j] * ig * (1.0f - ug * ug);
-          }
-        } else if (g == 1) {
-          const float4 gf = *reinterpret_cast<const float4*>(gs + 1 * NH + 4 * q);
+        for (int q = 0; q < EW / 4; ++q) {
           const float4 cp = *reinterpret_cast<const float4*>(k.c_prev + row * NH + e0 + 4 * q);
           float dcp[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float fg = f4get(gf, j);
+            const float fg = gf[4 * q + j];
             dz[4 * q + j] = dct[4 * q + j] * (f4get(cp, j) * nd) * fg * (1.0f - fg);
             dcp[j] = dct[4 * q + j] * fg * nd;
           }
           *reinterpret_cast<float4*>(k.dc_out + row * NH + e0 + 4 * q) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
-        } else {
-          const float4 go = *reinterpret_cast<const float4*>(gs + 2 * NH + 4 * q);
+        }
+      } else {
+        float go[EW];
+        ld_fm<EW>(gates_fm, 2 * NH + e0, B, b, go);
+#pragma unroll
+        for (int q = 0; q < EW / 4; ++q) {
           const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float og = f4get(go, j), tcv = ftanh(f4get(cc, j));
+            const float og = go[4 * q + j], tcv = ftanh(f4get(cc, j));
             dz[4 * q + j] = dh[4 * q + j] * tcv * og * (1.0f - og);
           }
         }
       }
-      store_vec<EW>(zo + g * NH, dz);
+      st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);
       if (k.dzT != nullptr) {                 // dz^T tile for the tensor-core wgrad: K-major over rows, hi | lo
         uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * 256 * 128);
 #pragma unroll
@@ -167,7 +175,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
     float dpm[EW];
 #pragma unroll
     for (int j = 0; j < EW; ++j) dpm[j] = 0.f;
-    float* dp = k.sv_dpre + row * 192 + e0;
+    uint8_t* dptile = (k.dpT != nullptr)
+        ? reinterpret_cast<uint8_t*>(k.dpT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * k.ndp * 128) : nullptr;
+    auto put_dp = [&](int n0, const float (&vals)[EW]) {        // encoder pre-activation grads as K-major tiles
+      if (dptile == nullptr) return;
+#pragma unroll
+      for (int j = 0; j < EW; ++j) {
+        const uint32_t off = tc::sw128_offset((uint32_t)(n0 + j), (uint32_t)lane);
+        const float hi = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
+        *reinterpret_cast<float*>(dptile + off) = hi;
+        *reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off) = vals[j] - hi;
+      }
+    };
 #pragma unroll
     for (int gp = 0; gp < NGRP; ++gp) {
       float d[EW];
@@ -185,36 +204,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         store_vec<EW>(k.dh_out + row * NH + e0, d);
       } else if (VAR == NMARL_NC || VAR == NMARL_IA2C) {
         float sv[EW];
-#pragma unroll
-        for (int q = 0; q < EW / 4; ++q) {
-          const float4 s4 = *reinterpret_cast<const float4*>(k.sv_sh + row * (SD + NH) + gp * NH + e0 + 4 * q);
-          sv[4 * q] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
-        }
+        ld_fm<EW>(sh_fm, gp * NH + e0, B, b, sv);
 #pragma unroll
         for (int j = 0; j < EW; ++j) d[j] = sv[j] > 0.f ? d[j] : 0.f;
-        store_vec<EW>(dp + gp * NH, d);
+        put_dp(gp * NH + e0, d);
         if (VAR == NMARL_NC && gp == 2) {
 #pragma unroll
           for (int j = 0; j < EW; ++j) dpm[j] = d[j];
         }
       } else {                                  // IC3 / DIAL: one 64-wide s
         float hx[EW], hm[EW], o[EW];
-#pragma unroll
-        for (int q = 0; q < EW / 4; ++q) {
-          const float4 a4 = *reinterpret_cast<const float4*>(k.sv_enc + row * 128 + e0 + 4 * q);
-          hx[4 * q] = a4.x; hx[4 * q + 1] = a4.y; hx[4 * q + 2] = a4.z; hx[4 * q + 3] = a4.w;
-          if (VAR == NMARL_DIAL) {
-            const float4 b4 = *reinterpret_cast<const float4*>(k.sv_enc + row * 128 + NH + e0 + 4 * q);
-            hm[4 * q] = b4.x; hm[4 * q + 1] = b4.y; hm[4 * q + 2] = b4.z; hm[4 * q + 3] = b4.w;
-          }
-        }
+        ld_fm<EW>(enc_fm, e0, B, b, hx);
+        if (VAR == NMARL_DIAL) ld_fm<EW>(enc_fm, NH + e0, B, b, hm);
 #pragma unroll
         for (int j = 0; j < EW; ++j) {
           if (VAR == NMARL_IC3) { o[j] = d[j] * (1.0f - hx[j] * hx[j]); dpm[j] = d[j]; }
           else { o[j] = hx[j] > 0.f ? d[j] : 0.f; dpm[j] = hm[j] > 0.f ? d[j] : 0.f; }
         }
-        store_vec<EW>(dp, o);
-        store_vec<EW>(dp + NH, dpm);
+        put_dp(e0, o);
+        put_dp(NH + e0, dpm);
       }
     }
     tc::fence_before_sync();

@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     const size_t row = (size_t)i * B + b;
     const float nd = 1.0f - a.done[b];
     const int LDI = m.kx_pad + m.kp_pad + m.km_pad;
-    float* xin_row = SAVE ? k.sv_xin + row * LDI : nullptr;
-    float* sh_row = SAVE ? k.sv_sh + row * (SD + NH) : nullptr;
+    // saved activations are feature-major on this path: [agent][feature][env]
+    float* xin_fm = SAVE ? k.sv_xin + (size_t)i * LDI * B : nullptr;
+    float* sh_fm = SAVE ? k.sv_sh + (size_t)i * (SD + NH) * B : nullptr;
+    float* enc_fm = (SAVE && k.sv_enc) ? k.sv_enc + (size_t)i * 128 * B : nullptr;
+    float* gates_fm = SAVE ? k.sv_gates + (size_t)i * NG * B : nullptr;
     long long* prof = (k.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1 && tid == 0) ? k.prof : nullptr;
     int pi_ = 0;
 #define STAMP() do { if (prof) prof[pi_++] = clock64(); } while (0)
@@ -176,17 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     }
     STAMP();
     // ---- encoder GEMMs: A chunks back to back, one completion wait ----------------------------------------------
-    float* xm = SAVE ? xin_row + m.kx_pad + m.kp_pad : nullptr;
-    if (SAVE && c0 < m.kx_pad) store_vec<W>(xin_row + c0, xv);
+    const int xm0 = m.kx_pad + m.kp_pad;
+    if (SAVE && c0 < m.kx_pad) st_fm<W>(xin_fm, c0, B, b, xv);
     produce_in(c, xv);
     if (VAR == NMARL_NC) {
-      if (SAVE && c0 < m.kp_pad) store_vec<W>(xin_row + m.kx_pad + c0, pv);
+      if (SAVE && c0 < m.kp_pad) st_fm<W>(xin_fm, m.kx_pad + c0, B, b, pv);
       produce_in(c, pv);
     }
     if (VAR == NMARL_IC3) {
 #pragma unroll
       for (int hb = 0; hb < 2; ++hb) {
-        if (SAVE) store_vec<W>(xm + hb * 32 + c0, mv[0][hb]);
+        if (SAVE) st_fm<W>(xin_fm, xm0 + hb * 32 + c0, B, b, mv[0][hb]);
         produce_in(c, mv[0][hb]);
       }
     } else if (VAR != NMARL_IA2C) {
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
               t[4 * q] = w.x; t[4 * q + 1] = w.y; t[4 * q + 2] = w.z; t[4 * q + 3] = w.w;
             }
           }
-          if (SAVE) store_vec<W>(xm + s * NH + hb * 32 + c0, t);
+          if (SAVE) st_fm<W>(xin_fm, xm0 + s * NH + hb * 32 + c0, B, b, t);
           produce_in(c, t);
         }
       }
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         float z[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) z[j] = 0.f;
-        for (int q = ag.n_nbr * 2; q < m.km_pad / 32; ++q) store_vec<W>(xm + q * 32 + c0, z);
+        for (int q = ag.n_nbr * 2; q < m.km_pad / 32; ++q) st_fm<W>(xin_fm, xm0 + q * 32 + c0, B, b, z);
       }
     }
     STAMP();
@@ -224,19 +227,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     float s0[EW];
     enc_load(c, ACC_COL, s0);
     bias_act(s0, P + ag.o_b_ob + e0, VAR == NMARL_IC3 ? 1 : 0);
-    if (SAVE && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) store_vec<EW>(k.sv_enc + row * 128 + e0, s0);
+    if (SAVE && (VAR == NMARL_IC3 || VAR == NMARL_DIAL)) st_fm<EW>(enc_fm, e0, B, b, s0);
     if (VAR == NMARL_NC) {
       float s1[EW], s2[EW];
       enc_load(c, ACC_COL + 64, s1);
       enc_load(c, ACC_COL + 128, s2);
       bias_act(s1, P + ag.o_b_fp + e0, 0);
       bias_act(s2, P + ag.o_b_msg + e0, 0);
-      if (SAVE) { store_vec<EW>(sh_row + e0, s0); store_vec<EW>(sh_row + NH + e0, s1); store_vec<EW>(sh_row + 2 * NH + e0, s2); }
+      if (SAVE) { st_fm<EW>(sh_fm, e0, B, b, s0); st_fm<EW>(sh_fm, NH + e0, B, b, s1); st_fm<EW>(sh_fm, 2 * NH + e0, B, b, s2); }
       produce_act(c, s0);
       produce_act(c, s1);
       produce_act(c, s2);
     } else if (VAR == NMARL_IA2C) {
-      if (SAVE) store_vec<EW>(sh_row + e0, s0);
+      if (SAVE) st_fm<EW>(sh_fm, e0, B, b, s0);
       produce_act(c, s0);
     } else {
       float s1[EW];
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         for (int j = 0; j < EW; ++j) s0[j] += s1[j];
       } else {                                                           // DIAL: relu + relu + onehot(argmax p_i)
         bias_act(s1, P + ag.o_b_msg + e0, 0);
-        if (SAVE) store_vec<EW>(k.sv_enc + row * 128 + NH + e0, s1);
+        if (SAVE) st_fm<EW>(enc_fm, NH + e0, B, b, s1);
         int am = 0;
         {
           const float* pr = a.fp + row * n_a;
@@ -257,12 +260,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < EW; ++j) s0[j] = (s0[j] + s1[j]) + ((e0 + j) == am ? 1.0f : 0.0f);
       }
-      if (SAVE) store_vec<EW>(sh_row + e0, s0);
+      if (SAVE) st_fm<EW>(sh_fm, e0, B, b, s0);
       produce_act(c, s0);
     }
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-      if (SAVE) store_vec<W>(sh_row + SD + hb * 32 + c0, hv[hb]);
+      if (SAVE) st_fm<W>(sh_fm, SD + hb * 32 + c0, B, b, hv[hb]);
       produce_in(c, hv[hb]);
     }
     STAMP();
@@ -308,8 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         store_vec<8>(a.h_out + row * NH + u0, hn);
       }
       if (SAVE) {
-        float* gs = k.sv_gates + row * NG + u0;
-        store_vec<8>(gs + 0 * NH, gi); store_vec<8>(gs + 1 * NH, gf); store_vec<8>(gs + 2 * NH, go); store_vec<8>(gs + 3 * NH, gu);
+        st_fm<8>(gates_fm, 0 * NH + u0, B, b, gi); st_fm<8>(gates_fm, 1 * NH + u0, B, b, gf);
+        st_fm<8>(gates_fm, 2 * NH + u0, B, b, go); st_fm<8>(gates_fm, 3 * NH + u0, B, b, gu);
       }
       STAMP();
       if (MODE != MODE_V) {

@@ -96,6 +96,18 @@ __device__ __forceinline__ void enc_load(RowCtx& c, uint32_t col, float (&v)[EW]
   }
   tc::fence_before_sync();
 }
+// feature-major saved activations [feature][env]: lane == env row, so one warp access per feature is a single
+// 128-byte line (the row-major form would touch 32 lines per access)
+template <int NV>
+__device__ __forceinline__ void st_fm(float* base, int f0, int B, int b, const float (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) base[(size_t)(f0 + j) * B + b] = v[j];
+}
+template <int NV>
+__device__ __forceinline__ void ld_fm(const float* base, int f0, int B, int b, float (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = base[(size_t)(f0 + j) * B + b];
+}
 template <int NV>
 __device__ __forceinline__ void store_vec(float* dst, const float (&s)[NV]) {
 #pragma unroll

@@ -1,25 +1,61 @@
-// tc_wgrad.cu -- tcgen05 weight gradient of the LSTM gate matrix:
-//   dW[ka][n] = sum over all (t, env) rows r of  [s | h^][r][ka] * dz[r][n]        (ka, n in [0, 256))
-// A 3xTF32 GEMM with M = ka (two 128-lane tiles), N = 256 and a contraction over rows split across CTAs
-// (fixed-order reduce afterwards).  The A operand is read straight from the row-major saved activations:
-// TMEM lane = ka, so for a fixed row the 32 lanes of a warp read 32 consecutive floats (coalesced), split
-// them hi/lo and tcgen05.st them.  The B operand (dz^T, K-major over rows) was written by the backward cell
-// kernel as ready-made [hi | lo] 128B-swizzled tiles, so the producer is one 64 KB bulk copy per 32 rows.
+// tc_wgrad.cu -- tcgen05 weight gradients of every GEMM of the cell (gate matrix and the obs / fingerprint /
+// message encoders):   dW[ka][n] = sum over all (t, env) rows r of  A[r][ka] * D[r][n]
+// as 3xTF32 GEMMs with M = ka (one 128-lane tile per job), the contraction over rows split across CTAs and a
+// fixed-order reduce afterwards.
+//   A operand: the saved activations are feature-major ([t][agent][feature][env]); TMEM lane = feature ka, so
+//              a thread reads 8 consecutive envs (32 contiguous bytes), splits hi/lo and tcgen05.st's them.
+//   B operand: D^T, K-major over rows, was written by the backward cell kernel as ready-made [hi | lo]
+//              128B-swizzled tiles (dz: 256 rows, encoder pre-activation grads: 192/128/64 rows); the producer
+//              bulk-copies the needed row range of the tile per 32 env rows.
+//   Biases:    the obs-encoder job carries an extra all-ones lane and spans every column of the dpre tile, which
+//              yields all encoder bias gradients for free; the gate bias is a coalesced column sum of dz.
 #include "bwd_common.cuh"
 #include "tc_row.cuh"
 
 namespace {
 using namespace tcrow;
 
+enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_P, J_ENC_M0, J_ENC_M1, J_COUNT };
+
 struct TcWgK {
-  int N, B, T, splits, i_lda;
-  const float* A;            // sv_sh   [T][N][B][lda]
-  const float* BT;           // dzT     [T][N][B/32][2][256][32]
-  float* ws;                 // [splits][N][257][256]
+  int B, T, splits, ndp;
+  const float* sv_sh; const float* sv_xin; const float* dzT; const float* dpT;
+  float* ws;
+  long long ws_off[J_COUNT];     // float offset of each job's partial block [splits][N_agents][128][N_job]
+  int jobs[J_COUNT]; int n_jobs; // job kinds present
   int* err;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ TcWgK k) {
+struct JobDesc {
+  const float* A; int F_A, a_feat0, ka_cnt, ones;
+  const float* BT; int tile_rows, n_row0, N;
+};
+
+__device__ __forceinline__ JobDesc job_desc(const nmarl_model& m, const TcWgK& k, int kind, int i) {
+  const nmarl_agent& ag = m.agent[i];
+  JobDesc d;
+  const int SD = m.s_dim, LDI = m.kx_pad + m.kp_pad + m.km_pad;
+  const int Km = (m.variant == NMARL_IC3) ? NH : ag.n_nbr * NH;
+  if (kind == J_GATE0 || kind == J_GATE1) {
+    const int mt = kind - J_GATE0;
+    d.A = k.sv_sh; d.F_A = SD + NH; d.a_feat0 = 128 * mt; d.ka_cnt = max(0, min(128, SD + NH - 128 * mt)); d.ones = 0;
+    d.BT = k.dzT; d.tile_rows = 256; d.n_row0 = 0; d.N = 256;
+  } else if (kind == J_ENC_X) {
+    d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = 0; d.ka_cnt = ag.x_nsrc * ag.x_w; d.ones = 1;
+    d.BT = k.dpT; d.tile_rows = k.ndp; d.n_row0 = 0; d.N = k.ndp;
+  } else if (kind == J_ENC_P) {
+    d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = m.kx_pad; d.ka_cnt = ag.n_nbr * m.n_a; d.ones = 0;
+    d.BT = k.dpT; d.tile_rows = k.ndp; d.n_row0 = 64; d.N = 64;
+  } else {
+    const int mt = kind - J_ENC_M0;
+    d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = m.kx_pad + m.kp_pad + 128 * mt; d.ka_cnt = max(0, min(128, Km - 128 * mt)); d.ones = 0;
+    d.BT = k.dpT; d.tile_rows = k.ndp; d.n_row0 = (m.variant == NMARL_NC) ? 128 : 64; d.N = 64;
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ nmarl_model m,
+                                                                 const __grid_constant__ TcWgK k) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
@@ -28,13 +64,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int mt = blockIdx.x & 1, sp = blockIdx.x >> 1, i = blockIdx.y;
+  const int sp = blockIdx.x, jslot = blockIdx.y, i = blockIdx.z;
+  const int kind = k.jobs[jslot];
+  const JobDesc d = job_desc(m, k, kind, i);
+  const int N_agents = m.n_agent;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kb_total = k.T * (k.B / 32);                              // 32-row k-blocks of this agent
+  const int bpt = k.B / 32;                                           // 32-row k-blocks per time step
+  const int kb_total = k.T * bpt;
   const int per = (kb_total + k.splits - 1) / k.splits;
   const int kb0 = sp * per, kb1 = min(kb_total, kb0 + per);
-  const int nkb = max(0, kb1 - kb0);
-  const int bpt = k.B / 32;                                           // k-blocks per time step
+  const int nkb = (d.ka_cnt > 0) ? max(0, kb1 - kb0) : 0;
+  float* wsj = k.ws + k.ws_off[jslot] + ((size_t)sp * N_agents + i) * 128 * d.N;
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
@@ -48,37 +88,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t tile_bytes = (uint32_t)d.N * 128u;                   // hi (or lo) part staged per k-block
 
   if (warp < ROW_THREADS / 32) {
     RowCtx c;
     const int set = warp >> 2, quarter = warp & 3;
-    const int ka = mt * 128 + quarter * 32 + lane;
+    const int ka = quarter * 32 + lane;                               // TMEM lane == feature within this M tile
     c.tmem = tmem; c.lane_base = (uint32_t)(quarter * 32) << 16;
     c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.set = set; c.err = k.err;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      const int t = kb / bpt, rb = kb - t * bpt;
-      const float* src = k.A + (((size_t)t * k.N + i) * k.B + rb * 32 + set * W) * k.i_lda + ka;
+    const bool real = ka < d.ka_cnt, one = d.ones && ka == d.ka_cnt;
+    for (int q = 0; q < nkb; ++q) {
+      const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
       float x[W];
+      if (real) {
+        const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + d.a_feat0 + ka) * k.B + rb * 32 + set * W;
 #pragma unroll
-      for (int j = 0; j < W; ++j) x[j] = src[(size_t)j * k.i_lda];
+        for (int p = 0; p < W / 4; ++p) {
+          const float4 v = *reinterpret_cast<const float4*>(src + 4 * p);
+          x[4 * p] = v.x; x[4 * p + 1] = v.y; x[4 * p + 2] = v.z; x[4 * p + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) x[j] = one ? 1.0f : 0.0f;
+      }
       produce_in(c, x);
     }
-    float* out = k.ws + (((size_t)sp * k.N + i) * 257 + ka) * 256 + set * 64;
-    if (nkb > 0) {
-      tc::mbar_wait(acc_full, 0, k.err, 13);
-      tc::fence_after_sync();
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        float v[8];
-        tc::tmem_ld8(tmem + c.lane_base + ACC_COL + set * 64 + 8 * p, v);
-        tc::wait_ld();
-        store_vec<8>(out + 8 * p, v);
+    // tcgen05.ld is warp-collective (.sync.aligned): the condition must be warp-uniform; stores are per lane
+    const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0);
+    if (warp_active) {
+      float* out = wsj + (size_t)ka * d.N;
+      if (nkb > 0) {
+        tc::mbar_wait(acc_full, 0, k.err, 13);
+        tc::fence_after_sync();
+        for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) {
+          float v[8];
+          tc::tmem_ld8(tmem + c.lane_base + ACC_COL + c0, v);
+          tc::wait_ld();
+          if (real || one) store_vec<8>(out + c0, v);
+        }
+        tc::fence_before_sync();
+      } else if (real || one) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) store_vec<8>(out + c0, z);
       }
-      tc::fence_before_sync();
-    } else {
-      float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int p = 0; p < 8; ++p) store_vec<8>(out + 8 * p, z);
     }
   } else if (warp == ROW_THREADS / 32) {
     if (lane == 0) {
@@ -86,19 +138,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const int kb = kb0 + q, st = q % S_STAGES;
         const int t = kb / bpt, rb = kb - t * bpt;
         tc::mbar_wait(&b_empty[st], ((q / S_STAGES) & 1) ^ 1, k.err, 21);
-        tc::mbar_arrive_expect_tx(&b_full[st], STAGE_BYTES);
-        tc::bulk_g2s(bst + st * STAGE_BYTES, k.BT + (((size_t)t * k.N + i) * bpt + rb) * (2 * 256 * 32), STAGE_BYTES, &b_full[st]);
+        tc::mbar_arrive_expect_tx(&b_full[st], 2 * tile_bytes);
+        const uint8_t* tile = reinterpret_cast<const uint8_t*>(d.BT) + (((size_t)t * N_agents + i) * bpt + rb) * (size_t)(2 * d.tile_rows * 128);
+        tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
+        tc::bulk_g2s(bst + st * STAGE_BYTES + tile_bytes, tile + (size_t)(d.tile_rows + d.n_row0) * 128, tile_bytes, &b_full[st]);
       }
     }
   } else {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_tf32(128, 256);
+      const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)d.N);
       for (int q = 0; q < nkb; ++q) {
         const int st = q % S_STAGES, slot = q & 1;
         tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 31);
         tc::mbar_wait(&a_full[slot], (q >> 1) & 1, k.err, 32);
         tc::fence_after_sync();
-        const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + 256 * 128);
+        const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile_bytes);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
@@ -116,71 +170,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
 }
 
-// column sums of dz (the gate bias gradient): [splits][N][256] partials, fixed-order
-__global__ void __launch_bounds__(256) dz_colsum_kernel(const float* __restrict__ dz, int N, int B, int T, int splits,
-                                                       float* __restrict__ part) {
-  const int sp = blockIdx.x, i = blockIdx.y, n = threadIdx.x;
-  const long R = (long)T * B;
-  const long per = ((R + splits - 1) / splits + 3) / 4 * 4;   // multiple of 4 so 4-row groups never straddle a time step
-  const long r0 = sp * per, r1 = min(R, r0 + per);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  long r = r0;
-  for (; r + 3 < r1; r += 4) {
-    const long t = r / B, b = r - t * B;              // B % 4 == 0: the 4 rows share t
-    const float* p = dz + (((size_t)t * N + i) * B + b) * NG + n;
-    s0 += p[0]; s1 += p[NG]; s2 += p[2 * NG]; s3 += p[3 * NG];
+// fixed-order reduce over the row splits + scatter into the flat gradient buffer
+__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_constant__ nmarl_model m, const __grid_constant__ TcWgK k,
+                                                             float* __restrict__ grads) {
+  const int jslot = blockIdx.y, i = blockIdx.z, kind = k.jobs[jslot];
+  const JobDesc d = job_desc(m, k, kind, i);
+  const nmarl_agent& ag = m.agent[i];
+  const int lanes = d.ka_cnt + (d.ones ? 1 : 0);
+  const int total = lanes * d.N;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int ln = e / d.N, n = e - ln * d.N;
+    float s = 0.f;
+    for (int sp = 0; sp < k.splits; ++sp) s += k.ws[k.ws_off[jslot] + (((size_t)sp * m.n_agent + i) * 128 + ln) * d.N + n];
+    if (kind == J_GATE0 || kind == J_GATE1) grads[ag.o_wxh + (size_t)(128 * (kind - J_GATE0) + ln) * NG + n] = s;
+    else if (kind == J_ENC_X) {
+      if (ln < d.ka_cnt) { if (n < NH) grads[ag.o_w_ob + ln * NH + n] = s; }
+      else if (n < NH) grads[ag.o_b_ob + n] = s;                                       // ones lane: biases
+      else if (m.variant == NMARL_NC && n < 2 * NH) grads[ag.o_b_fp + n - NH] = s;
+      else grads[ag.o_b_msg + n - ((m.variant == NMARL_NC) ? 2 * NH : NH)] = s;
+    } else if (kind == J_ENC_P) grads[ag.o_w_fp + ln * NH + n] = s;
+    else grads[ag.o_w_msg + (size_t)(128 * (kind - J_ENC_M0) + ln) * NH + n] = s;
   }
-  for (; r < r1; ++r) {
-    const long t = r / B, b = r - t * B;
-    s0 += dz[(((size_t)t * N + i) * B + b) * NG + n];
-  }
-  part[((size_t)sp * N + i) * NG + n] = (s0 + s1) + (s2 + s3);
 }
-__global__ void dz_colsum_reduce_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ part, int splits,
-                                        float* __restrict__ grads) {
-  const int i = blockIdx.x, n = threadIdx.x;
+
+// gate bias gradient: column sums of the feature-major dz (one CTA per (agent, gate column); coalesced)
+__global__ void __launch_bounds__(256) dz_colsum_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ dz,
+                                                       int B, int T, float* __restrict__ grads) {
+  __shared__ float red[8];
+  const int n = blockIdx.x, i = blockIdx.y;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += part[((size_t)sp * m.n_agent + i) * NG + n];
-  grads[m.agent[i].o_b + n] = s;
+  for (int t = 0; t < T; ++t) {
+    const float* p = dz + (((size_t)t * m.n_agent + i) * NG + n) * B;
+    for (int b = threadIdx.x; b < B; b += 256) s += p[b];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < 8; ++w) tsum += red[w];
+    grads[m.agent[i].o_b + n] = tsum;
+  }
+}
+
+int job_list(const nmarl_model* m, int* jobs) {
+  int n = 0;
+  jobs[n++] = J_GATE0;
+  if (m->s_dim + NH > 128) jobs[n++] = J_GATE1;
+  jobs[n++] = J_ENC_X;
+  if (m->variant == NMARL_NC) jobs[n++] = J_ENC_P;
+  if (m->variant != NMARL_IA2C) {
+    jobs[n++] = J_ENC_M0;
+    if (m->km_pad > 128) jobs[n++] = J_ENC_M1;
+  }
+  return n;
+}
+int job_N(const nmarl_model* m, int kind) {
+  if (kind == J_GATE0 || kind == J_GATE1) return 256;
+  if (kind == J_ENC_X) return nmarl_tc_ndp(m);
+  return 64;
 }
 
 }  // namespace
 
+int nmarl_tc_ndp(const nmarl_model* m) { return m->variant == NMARL_NC ? 192 : (m->variant == NMARL_IA2C ? 64 : 128); }
+
 int nmarl_tc_wgrad_splits(int n_agent) {
-  // 2 M-tiles x splits x agents CTAs: a whole number of waves of 148 SMs when possible
-  int s = 37;
+  int s = 37;                                   // 2 gate tiles x 37 x 8 agents = 592 CTAs = 4 waves of 148 SMs
   while (2 * s * n_agent > 148 * 8 && s > 1) s = (s + 1) / 2;
   return s;
 }
 
 int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
-  return (int64_t)nmarl_tc_wgrad_splits(m->n_agent) * m->n_agent * 257 * 256 + (int64_t)64 * m->n_agent * NG;
+  int jobs[J_COUNT];
+  const int nj = job_list(m, jobs);
+  int64_t tot = 0;
+  for (int j = 0; j < nj; ++j) tot += (int64_t)nmarl_tc_wgrad_splits(m->n_agent) * m->n_agent * 128 * job_N(m, jobs[j]);
+  return tot;
 }
 
-// gate wgrad on tensor cores.  ws must hold nmarl_tc_wgrad_ws_floats(m) floats.
-int nmarl_tc_launch_gate_wgrad(const nmarl_model* m, int B, int T, const float* sv_sh, const float* dzT, const float* sv_dz,
-                               float* ws, int* err, int* splits_out, cudaStream_t st) {
+int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st) {
   TcWgK k{};
-  k.N = m->n_agent; k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.i_lda = m->s_dim + NH;
-  k.A = sv_sh; k.BT = dzT; k.ws = ws; k.err = err;
+  k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
+  k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
+  k.n_jobs = job_list(m, k.jobs);
+  long long off = 0;
+  for (int j = 0; j < k.n_jobs; ++j) { k.ws_off[j] = off; off += (long long)k.splits * m->n_agent * 128 * job_N(m, k.jobs[j]); }
   static bool configured = false;
   if (!configured) {
     NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
-  tc_wgrad_kernel<<<dim3(2 * k.splits, m->n_agent), TC_THREADS, TC_SMEM, st>>>(k);
+  tc_wgrad_kernel<<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
-  *splits_out = k.splits;
-  // bias: column sums of dz
-  float* part = ws + (size_t)k.splits * m->n_agent * 257 * 256;
-  dz_colsum_kernel<<<dim3(64, m->n_agent), 256, 0, st>>>(sv_dz, m->n_agent, B, T, 64, part);
+  NMARL_DBG_SYNC(st, "tc_wgrad_kernel");
+  tc_wgrad_reduce_kernel<<<dim3(64, k.n_jobs, m->n_agent), 256, 0, st>>>(*m, k, grads);
   NMARL_LAUNCH_CHECK();
-  return 0;
-}
-
-int nmarl_tc_launch_bias_reduce(const nmarl_model* m, const float* ws, int splits, float* grads, cudaStream_t st) {
-  const float* part = ws + (size_t)splits * m->n_agent * 257 * 256;
-  dz_colsum_reduce_kernel<<<m->n_agent, 256, 0, st>>>(*m, part, 64, grads);
+  NMARL_DBG_SYNC(st, "tc_wgrad_reduce");
+  dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st>>>(*m, sv_dz, B, T, grads);
   NMARL_LAUNCH_CHECK();
   return 0;
 }

@@ -888,6 +888,8 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     k.wpack = a->wpack; k.tc_err = a->tc_err;
     const bool use_tc = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
     k.dzT = (use_tc && a->sv_dzT) ? a->sv_dzT + (size_t)t * N * (B / 32) * (2 * 256 * 32) : nullptr;
+    k.ndp = nmarl_tc_ndp(m);
+    k.dpT = (use_tc && a->sv_dpT) ? a->sv_dpT + (size_t)t * N * (B / 32) * (2 * k.ndp * 32) : nullptr;
     int rc = 0;
     if (use_tc) rc = nmarl_tc_launch_bwd(m, k, st);
     else
@@ -898,6 +900,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
       case NMARL_DIAL: rc = launch_bwd<NMARL_DIAL>(m, k, st); break;
     }
     if (rc) return rc;
+    NMARL_DBG_SYNC(st, "cell_bwd");
     if (m->variant == NMARL_DIAL) {
       dim3 grid((B + 63) / 64, N);
       dial_msg_bwd_kernel<64, 16><<<grid, 256, 0, st>>>(*m, B, a->wt, a->msg_seq + (size_t)t * nb * NH, k.dmsg_out,
@@ -908,32 +911,29 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   // 3. weight gradients
   int Ka[NMARL_MAX_AGENT], ow[NMARL_MAX_AGENT], ob[NMARL_MAX_AGENT];
   const int LDI = m->kx_pad + m->kp_pad + m->km_pad;
-  const bool tc_wg = (a->wpack != nullptr && a->sv_dzT != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32 && SD + NH == 256);
-  for (int i = 0; i < N; ++i) { Ka[i] = SD + NH; ow[i] = m->agent[i].o_wxh; ob[i] = m->agent[i].o_b; }
+  const bool tc_wg = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
   if (tc_wg) {
+    NMARL_CHECK(a->sv_dzT && a->sv_dpT, "a2c_bptt: tensor-core path needs sv_dzT / sv_dpT");
     NMARL_CHECK(nmarl_tc_wgrad_ws_floats(m) <= a->ws_floats, "tc wgrad: workspace too small");
-    int splits = 0;
-    if (nmarl_tc_launch_gate_wgrad(m, B, T, a->sv_sh, a->sv_dzT, a->sv_dz, a->ws, a->tc_err, &splits, st)) return 1;
-    WgRedK r{};
-    r.N = N; r.splits = splits; r.ka_max = 256; r.nd = NG; r.ws = a->ws; r.grads = a->grads;
-    for (int i = 0; i < N; ++i) { r.Ka[i] = 256; r.o_w[i] = ow[i]; r.o_b[i] = -1; }
-    wgrad_reduce_kernel<<<dim3((257 * NG + 255) / 256, N), 256, 0, st>>>(r);
-    NMARL_LAUNCH_CHECK();
-    if (nmarl_tc_launch_bias_reduce(m, a->ws, splits, a->grads, st)) return 1;
-  } else if (run_wgrad(m, a, 4, a->sv_sh, SD + NH, 0, a->sv_dz, NG, 0, Ka, ow, ob, st)) return 1;
-  for (int i = 0; i < N; ++i) { Ka[i] = m->agent[i].x_nsrc * m->agent[i].x_w; ow[i] = m->agent[i].o_w_ob; ob[i] = m->agent[i].o_b_ob; }
-  if (run_wgrad(m, a, 1, a->sv_xin, LDI, 0, a->sv_dpre, 192, 0, Ka, ow, ob, st)) return 1;
-  if (m->variant == NMARL_NC) {
-    for (int i = 0; i < N; ++i) { Ka[i] = m->agent[i].n_nbr * m->n_a; ow[i] = m->agent[i].o_w_fp; ob[i] = m->agent[i].o_b_fp; }
-    if (run_wgrad(m, a, 1, a->sv_xin, LDI, m->kx_pad, a->sv_dpre, 192, NH, Ka, ow, ob, st)) return 1;
-  }
-  if (m->variant != NMARL_IA2C) {
-    for (int i = 0; i < N; ++i) {
-      Ka[i] = (m->variant == NMARL_IC3) ? NH : m->agent[i].n_nbr * NH;
-      ow[i] = m->agent[i].o_w_msg; ob[i] = m->agent[i].o_b_msg;
+    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st)) return 1;
+    NMARL_DBG_SYNC(st, "tc_wgrads");
+  } else {
+    for (int i = 0; i < N; ++i) { Ka[i] = SD + NH; ow[i] = m->agent[i].o_wxh; ob[i] = m->agent[i].o_b; }
+    if (run_wgrad(m, a, 4, a->sv_sh, SD + NH, 0, a->sv_dz, NG, 0, Ka, ow, ob, st)) return 1;
+    for (int i = 0; i < N; ++i) { Ka[i] = m->agent[i].x_nsrc * m->agent[i].x_w; ow[i] = m->agent[i].o_w_ob; ob[i] = m->agent[i].o_b_ob; }
+    if (run_wgrad(m, a, 1, a->sv_xin, LDI, 0, a->sv_dpre, 192, 0, Ka, ow, ob, st)) return 1;
+    if (m->variant == NMARL_NC) {
+      for (int i = 0; i < N; ++i) { Ka[i] = m->agent[i].n_nbr * m->n_a; ow[i] = m->agent[i].o_w_fp; ob[i] = m->agent[i].o_b_fp; }
+      if (run_wgrad(m, a, 1, a->sv_xin, LDI, m->kx_pad, a->sv_dpre, 192, NH, Ka, ow, ob, st)) return 1;
     }
-    if (run_wgrad(m, a, 1, a->sv_xin, LDI, m->kx_pad + m->kp_pad, a->sv_dpre, 192, (m->variant == NMARL_NC) ? 2 * NH : NH,
-                  Ka, ow, ob, st)) return 1;
+    if (m->variant != NMARL_IA2C) {
+      for (int i = 0; i < N; ++i) {
+        Ka[i] = (m->variant == NMARL_IC3) ? NH : m->agent[i].n_nbr * NH;
+        ow[i] = m->agent[i].o_w_msg; ob[i] = m->agent[i].o_b_msg;
+      }
+      if (run_wgrad(m, a, 1, a->sv_xin, LDI, m->kx_pad + m->kp_pad, a->sv_dpre, 192, (m->variant == NMARL_NC) ? 2 * NH : NH,
+                    Ka, ow, ob, st)) return 1;
+    }
   }
   if (m->variant == NMARL_DIAL) {
     for (int i = 0; i < N; ++i) { Ka[i] = NH; ow[i] = m->agent[i].o_mfc_w; ob[i] = m->agent[i].o_mfc_b; }

@@ -200,6 +200,10 @@ typedef struct {
   const float* wpack;        /* packed tensor-core operands or NULL (see nmarl_fwd_args)            */
   int32_t* tc_err;
   float* sv_dzT;             /* tensor-core path: dz^T as [T][N][B/32][hi|lo][256][32] swizzled tiles  */
+  float* sv_dpT;             /* tensor-core path: encoder pre-activation grads^T, [T][N][B/32][hi|lo][ndp][32],
+                                ndp = 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C).  On the tensor-core path (wpack set,
+                                B % 128 == 0) sv_xin / sv_sh / sv_gates / sv_enc / sv_dz are FEATURE-MAJOR
+                                [T][N][feature][B] and sv_dpre is unused.                                          */
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */
