@@ -159,6 +159,7 @@ def main():
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
+    os.environ['NCCL_DEBUG'] = os.environ.get('NMARL_NCCL_DEBUG', 'WARN')     # keep stdout to the one JSON line
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -258,15 +259,19 @@ def main():
     peak = float(peaks.get('hbm_gbs', 6650.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('cell_fwd_p_bytes_per_launch')
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(
+            'tc_cell_fwd_p_bytes_per_launch' if e.use_tc else 'cell_fwd_p_bytes_per_launch')
     except Exception:
         pass
     achieved = alg_bytes / (ms_k * 1e-3) / 1e9
-    roofline = {'kernel': 'cell_fwd_kernel<NC,P> (fused gather+encoders+LSTM cell+heads+sampling)', 'bound': 'hbm',
+    roofline = {'kernel': ('tc_cell_fwd_kernel<P> (tcgen05 3xTF32: fused gather+encoders+LSTM cell+heads+sampling)'
+                           if e.use_tc else 'cell_fwd_kernel<P> (FP32 FFMA)'), 'bound': 'hbm',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                 'us_per_launch': ms_k * 1e3, 'algorithmic_bytes_per_launch': alg_bytes,
                 'peak_source': 'MEASURED_PEAKS.json (burst)' if peaks else 'fallback 6.65 TB/s',
-                'note': 'FP32 FFMA GEMMs (74 kMAC per agent-step): this kernel is compute-bound, see DESIGN.md'}
+                'tensor_tflops_3xtf32': 3 * 2 * 74359 * N * B / (ms_k * 1e-3) / 1e12,
+                'note': 'algorithmic bytes per SURVEY 8(d) (1640 B per agent-env-step); the kernel issues 3 TF32 MMAs per '
+                        'fp32 product (148.7 kFLOP fp32-equivalent per agent-step), see DESIGN.md'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -286,7 +291,12 @@ def main():
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_per_update * args.steps,
             'roofline': roofline, 'cpu_baseline': cpu}))
     if world > 1:
-        dist.destroy_process_group()
+        # captured CUDA graphs hold NCCL kernels: tearing the communicator down under them can block, so leave
+        # together after a final barrier instead of destroy_process_group()
+        sys.stdout.flush()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == '__main__':

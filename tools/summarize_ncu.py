@@ -45,7 +45,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__pcsamp_warps_issue_stalled_not_selected', 'smsp__pcsamp_warps_issue_stalled_selected',
         'smsp__pcsamp_warps_issue_stalled_wait', 'smsp__pcsamp_warps_issue_stalled_mio_throttle']
 traffic = {}
-for which in ('fwd', 'bwd'):
+for which in ('fwd', 'bwd', 'tc'):
     rep = 'gpurun_out/prof_%s_%s.ncu-rep' % (which, tag)
     if not os.path.exists(rep):
         continue
@@ -69,6 +69,17 @@ for which in ('fwd', 'bwd'):
             traffic[name.replace('void ', '').replace('<unnamed>::', '')] = tr
     print(open('profiles/%s_%s_full.txt' % (tag, which)).read()[:3000])
 if traffic:
+    old = {}
+    try:
+        old = json.load(open('profiles/traffic.json'))
+    except Exception:
+        pass
     p = [v for k, v in traffic.items() if k.startswith('cell_fwd_kernel<1, 0')]
-    json.dump({'tag': tag, 'per_kernel_bytes_per_launch': traffic,
-               'cell_fwd_p_bytes_per_launch': p[0] if p else None}, open('profiles/traffic.json', 'w'), indent=1)
+    ptc = [v for k, v in traffic.items() if k.startswith('tc_cell_fwd_kernel<1, 0')]
+    old.setdefault('per_kernel_bytes_per_launch', {}).update(traffic)
+    old['tag'] = tag
+    if p:
+        old['cell_fwd_p_bytes_per_launch'] = p[0]
+    if ptc:
+        old['tc_cell_fwd_p_bytes_per_launch'] = ptc[0]
+    json.dump(old, open('profiles/traffic.json', 'w'), indent=1)
