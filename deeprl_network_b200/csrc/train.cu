@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
 
 // Heads + A2C loss terms + d(loss)/d(logits, v) from the saved h sequence (thread == env row); used when the
 // rollout already saved the cell activations.  Same arithmetic as the TRAIN epilogue of the forward kernels.
-struct HeadFwdK {
-  int B, loss_tiles;
+struct HeadFwdK {                 // pointers are for step 0; blockIdx.z = t strides them
+  int B, N, loss_tiles;
   const float* params; const float* h1; const int32_t* act; const float* Rs; const float* Advs;
   float* sv_dlv; float* loss_part;
   float loss_scale, v_coef, e_coef;
@@ -605,13 +605,14 @@ struct HeadFwdK {
 
 __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant__ nmarl_model m, const __grid_constant__ HeadFwdK k) {
   __shared__ float red[3][4];
-  const int i = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x, B = k.B;
+  const int i = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x, B = k.B, t = blockIdx.z;
   const nmarl_agent& ag = m.agent[i];
   const int n_a = m.n_a;
   const float* __restrict__ P = k.params;
   float l_pol = 0.f, l_val = 0.f, l_ent = 0.f;
+  const size_t tb = (size_t)t * k.N * B;                    // step offset in rows
   if (b < B) {
-    const size_t row = (size_t)i * B + b;
+    const size_t row = tb + (size_t)i * B + b;
     float logit[NMARL_MAX_NA];
 #pragma unroll
     for (int cc = 0; cc < NMARL_MAX_NA; ++cc) logit[cc] = 0.f;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant_
       if (cc < n_a) { pi[cc] = expf(logit[cc] - mx); se += pi[cc]; } else pi[cc] = 0.f;
 #pragma unroll
     for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) pi[cc] = pi[cc] / se;
-    for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + k.act[(size_t)ag.nbr[s] * B + b]);
+    for (int s = 0; s < ag.n_nbr; ++s) v += __ldg(P + ag.o_v_w + NH + s * n_a + k.act[tb + (size_t)ag.nbr[s] * B + b]);
     v += __ldg(P + ag.o_v_b);
     const int act = k.act[row];
     const float R = k.Rs[row], Adv = k.Advs[row], cs = k.loss_scale;
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant_
   __syncthreads();
   if (threadIdx.x < 3) {
     const float s = ((red[threadIdx.x][0] + red[threadIdx.x][1]) + red[threadIdx.x][2]) + red[threadIdx.x][3];
-    float* lp = k.loss_part + ((size_t)i * k.loss_tiles + 2 * blockIdx.x) * 4;
+    float* lp = k.loss_part + (((size_t)t * k.N + i) * k.loss_tiles + 2 * blockIdx.x) * 4;
     lp[threadIdx.x] = s;
     if (2 * blockIdx.x + 1 < k.loss_tiles) lp[4 + threadIdx.x] = 0.f;
   }
@@ -828,15 +829,13 @@ extern "C" int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args*
   const int N = m->n_agent, B = a->B, T = a->T;
   const size_t nb = (size_t)N * B;
   const int tiles = nmarl_fwd_tiles(B);
-  for (int t = 0; t < T; ++t) {
-    HeadFwdK k{};
-    k.B = B; k.loss_tiles = tiles; k.params = a->params;
-    k.h1 = a->h_seq + (size_t)(t + 1) * nb * NH;
-    k.act = a->act + (size_t)t * nb; k.Rs = a->Rs + (size_t)t * nb; k.Advs = a->Advs + (size_t)t * nb;
-    k.sv_dlv = a->sv_dlv + (size_t)t * nb * 8; k.loss_part = a->loss_part + (size_t)t * N * tiles * 4;
-    k.loss_scale = 1.0f / ((float)T * (float)a->B_total); k.v_coef = a->v_coef; k.e_coef = a->e_coef;
-    train_heads_kernel<<<dim3((B + 127) / 128, N), 128, 0, st>>>(*m, k);
-  }
+  HeadFwdK k{};
+  k.B = B; k.N = N; k.loss_tiles = tiles; k.params = a->params;
+  k.h1 = a->h_seq + nb * NH;                                  // h after step t = h_seq[t + 1]
+  k.act = a->act; k.Rs = a->Rs; k.Advs = a->Advs;
+  k.sv_dlv = a->sv_dlv; k.loss_part = a->loss_part;
+  k.loss_scale = 1.0f / ((float)T * (float)a->B_total); k.v_coef = a->v_coef; k.e_coef = a->e_coef;
+  train_heads_kernel<<<dim3((B + 127) / 128, N, T), 128, 0, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   return 0;
 }
