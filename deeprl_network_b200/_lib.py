@@ -53,7 +53,8 @@ class FwdArgs(C.Structure):
                 ('pi', C.c_void_p), ('action', C.c_void_p), ('sample_mode', C.c_int32),
                 ('uniforms', C.c_void_p), ('rng', C.c_void_p), ('rng_offset', C.c_uint64),
                 ('act_in', C.c_void_p), ('v', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
-                ('sv_xin', C.c_void_p), ('sv_sh', C.c_void_p), ('sv_gates', C.c_void_p), ('sv_enc', C.c_void_p)]
+                ('sv_xin', C.c_void_p), ('sv_sh', C.c_void_p), ('sv_gates', C.c_void_p), ('sv_enc', C.c_void_p),
+                ('state_fm', C.c_int32)]
 
 
 class BwdArgs(C.Structure):
@@ -67,7 +68,7 @@ class BwdArgs(C.Structure):
                 ('dh_rec', C.c_void_p), ('dc_rec', C.c_void_p), ('dmsg', C.c_void_p),
                 ('wt', C.c_void_p), ('ws', C.c_void_p), ('ws_floats', C.c_int64),
                 ('loss_part', C.c_void_p), ('grads', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
-                ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p)]
+                ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p), ('state_fm', C.c_int32)]
 
 
 _lib = None

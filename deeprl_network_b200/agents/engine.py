@@ -49,11 +49,15 @@ class PolicyEngine:
         self.use_tc = bool(use_tc) and (self.B % 128 == 0)
         self.wpack = torch.zeros(layout.n_wp, **f32) if self.use_tc else None
         self.tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.c = [torch.zeros(N, B, NH, **f32) for _ in range(2)]
-        self.h = [torch.zeros(N, B, NH, **f32) for _ in range(2)]
+        # tensor-core path: LSTM state (and its gradients) feature-major [N,64,B] so that lane == env accesses are
+        # coalesced; DIAL keeps env-major state (its message kernels are env-major)
+        self.state_fm = self.use_tc and self.variant != 'ma2c_dial' and os.environ.get('NMARL_NO_STATE_FM', '0') != '1'
+        self._sshape = (N, NH, B) if self.state_fm else (N, B, NH)
+        self.c = [torch.zeros(*self._sshape, **f32) for _ in range(2)]
+        self.h = [torch.zeros(*self._sshape, **f32) for _ in range(2)]
         self.msg = [torch.zeros(N, B, NH, **f32) for _ in range(2)] if self.variant == 'ma2c_dial' else [None, None]
         self.cur = 0
-        self.c_bw, self.h_bw = torch.zeros(N, B, NH, **f32), torch.zeros(N, B, NH, **f32)
+        self.c_bw, self.h_bw = torch.zeros(*self._sshape, **f32), torch.zeros(*self._sshape, **f32)
         S = layout.obs_stride
         self.obs_buf = torch.zeros(T + 1, N, B, S, **f32)
         self.fp_buf = torch.full((T + 1, N, B, self.n_a), 1.0 / self.n_a, **f32)
@@ -96,7 +100,7 @@ class PolicyEngine:
             for t in (self.c[self.cur], self.h[self.cur], self.c_bw, self.h_bw):
                 t.zero_()
         else:
-            keep = (1.0 - mask)[None, :, None]
+            keep = (1.0 - mask)[None, None, :] if self.state_fm else (1.0 - mask)[None, :, None]
             for t in (self.c[self.cur], self.h[self.cur], self.c_bw, self.h_bw):
                 t.mul_(keep)
         self._refresh_msg()
@@ -130,10 +134,16 @@ class PolicyEngine:
             self.cur = 0
 
     def get_states_fw(self):
-        """[N, B, 128] = [c | h] like the reference's states_fw."""
-        return torch.cat([self.c[self.cur], self.h[self.cur]], dim=-1)
+        """[N, B, 128] = [c | h] like the reference's states_fw (env-major view whatever the device layout)."""
+        c, h = self.c[self.cur], self.h[self.cur]
+        if self.state_fm:
+            c, h = c.permute(0, 2, 1), h.permute(0, 2, 1)
+        return torch.cat([c, h], dim=-1).contiguous()
 
     def set_states(self, c, h, bw=True):
+        """c, h: env-major [N, B, 64]."""
+        if self.state_fm:
+            c, h = c.permute(0, 2, 1), h.permute(0, 2, 1)
         self.c[self.cur].copy_(c); self.h[self.cur].copy_(h)
         if bw:
             self.c_bw.copy_(c); self.h_bw.copy_(h)
@@ -145,7 +155,7 @@ class PolicyEngine:
         a.B = self.B
         a.params, a.obs, a.fp, a.done = L.ptr(self.params), L.ptr(obs), L.ptr(fp), L.ptr(done)
         a.c_in, a.h_in, a.msg_in = L.ptr(self.c[self.cur]), L.ptr(self.h[self.cur]), L.ptr(self.msg[self.cur])
-        a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
+        a.wpack, a.tc_err, a.state_fm = L.ptr(self.wpack), L.ptr(self.tc_err), int(self.state_fm)
         return a
 
     def step_p(self, obs, fp, done, pi_out, action_out=None, sample_mode=L.SAMPLE_NONE, uniforms=None, rng_offset=0):
@@ -209,7 +219,7 @@ class PolicyEngine:
         a = L.FwdArgs()
         a.B = self.B
         a.params, a.obs, a.fp, a.done = L.ptr(self.params), L.ptr(obs), L.ptr(fp), L.ptr(done)
-        a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
+        a.wpack, a.tc_err, a.state_fm = L.ptr(self.wpack), L.ptr(self.tc_err), int(self.state_fm)
         ms = self.msg_seq
         if which == 'p':
             a.c_in, a.h_in, a.msg_in = L.ptr(self.c_seq[t]), L.ptr(self.h_seq[t]), L.ptr(None if ms is None else ms[t])
@@ -273,7 +283,7 @@ class PolicyEngine:
         lay, N, B, T, dev = self.layout, self.N, self.B, self.T, self.device
         f32 = dict(dtype=torch.float32, device=dev)
         z = lambda *s: torch.zeros(*s, **f32)
-        self.h_seq, self.c_seq = z(T + 2, N, B, NH), z(T + 2, N, B, NH)       # +1 slot for the bootstrap p-call
+        self.h_seq, self.c_seq = z(T + 2, *self._sshape), z(T + 2, *self._sshape)       # +1 slot for the bootstrap p-call
         self.msg_seq = z(T + 2, N, B, NH) if self.variant == 'ma2c_dial' else None
         self.sv_xin = z(T, N, B, lay.ld_in)
         self.sv_sh = z(T, N, B, lay.s_dim + NH)
@@ -287,8 +297,8 @@ class PolicyEngine:
         self.sv_dzT = z(T, N, B // 32, 2 * 256 * 32) if self.use_tc else None
         self.sv_dpT = z(T, N, B // 32, 2 * ndp * 32) if self.use_tc else None
         self.sv_dmp = z(T, N, B, NH) if self.variant == 'ma2c_dial' else None
-        self.dh_rec, self.dc_rec = z(2, N, B, NH), z(2, N, B, NH)
-        self.dmsg = z(2, N, L.MAX_NBR, B, NH) if self.variant != 'ia2c' else None
+        self.dh_rec, self.dc_rec = z(2, *self._sshape), z(2, *self._sshape)
+        self.dmsg = z(2, N, L.MAX_NBR, *self._sshape[1:]) if self.variant != 'ia2c' else None
         self.ws_floats = int(L.lib().nmarl_ws_floats(C.byref(self.model), B, T))
         self.ws = z(max(self.ws_floats, 4))
         self.tiles = int(L.lib().nmarl_loss_tiles(C.byref(self.model), B))
@@ -311,6 +321,7 @@ class PolicyEngine:
         a.loss_part, a.grads = L.ptr(self.loss_part), L.ptr(self.grads)
         a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
         a.sv_dzT, a.sv_dpT = L.ptr(self.sv_dzT), L.ptr(self.sv_dpT)
+        a.state_fm = int(self.state_fm)
         return a
 
     def backward(self):

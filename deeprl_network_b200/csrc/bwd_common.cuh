@@ -15,6 +15,7 @@ struct BwdK {
   const float* wpack; int* tc_err;                                     // tcgen05 path (NULL -> FFMA)
   float* dzT;                                                          // step t: [N][B/32][hi|lo][256][32] tiles or NULL
   float* dpT;                                                          // step t: [N][B/32][hi|lo][ndp][32] tiles (encoder pre-act grads)
+  int state_fm;                                                        // c/dh/dc/dmsg tensors are feature-major
   int ndp;                                                             // rows of a dpT tile: 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C)
 };
 

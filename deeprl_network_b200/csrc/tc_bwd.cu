@@ -10,7 +10,7 @@
 namespace {
 using namespace tcrow;
 
-template <int VAR>
+template <int VAR, bool FM>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid_constant__ nmarl_model m,
                                                                     const __grid_constant__ BwdK k) {
   extern __shared__ uint8_t smem_raw[];
@@ -85,35 +85,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         dct[j] = 0.f;
       }
       if (k.has_next) {
+        float t16[EW];
+        ld_state<FM, EW>(k.dh_in, (size_t)i, b, e0, B, t16);
 #pragma unroll
-        for (int q = 0; q < EW / 4; ++q) {
-          const float4 r4 = *reinterpret_cast<const float4*>(k.dh_in + row * NH + e0 + 4 * q);
-          dh[4 * q] += r4.x; dh[4 * q + 1] += r4.y; dh[4 * q + 2] += r4.z; dh[4 * q + 3] += r4.w;
-          const float4 c4 = *reinterpret_cast<const float4*>(k.dc_in + row * NH + e0 + 4 * q);
-          dct[4 * q] = c4.x; dct[4 * q + 1] = c4.y; dct[4 * q + 2] = c4.z; dct[4 * q + 3] = c4.w;
-        }
+        for (int j = 0; j < EW; ++j) dh[j] += t16[j];
+        ld_state<FM, EW>(k.dc_in, (size_t)i, b, e0, B, dct);
         if (VAR == NMARL_NC || VAR == NMARL_IC3) {
           for (int s = 0; s < ag.n_recv; ++s) {
-            const float* mp = k.dmsg_in + (((size_t)ag.recv_agent[s] * NMARL_MAX_NBR + ag.recv_slot[s]) * B + b) * NH + e0;
+            ld_state<FM, EW>(k.dmsg_in, (size_t)ag.recv_agent[s] * NMARL_MAX_NBR + ag.recv_slot[s], b, e0, B, t16);
 #pragma unroll
-            for (int q = 0; q < EW / 4; ++q) {
-              const float4 m4 = *reinterpret_cast<const float4*>(mp + 4 * q);
-              dh[4 * q] += m4.x; dh[4 * q + 1] += m4.y; dh[4 * q + 2] += m4.z; dh[4 * q + 3] += m4.w;
-            }
+            for (int j = 0; j < EW; ++j) dh[j] += t16[j];
           }
         }
       }
       // dc_t += dh * o * (1 - tanh(c_t)^2)
-      float gov[EW];
+      float gov[EW], ccv[EW];
       ld_fm<EW>(gates_fm, 2 * NH + e0, B, b, gov);
+      ld_state<FM, EW>(k.c_cur, (size_t)i, b, e0, B, ccv);
 #pragma unroll
-      for (int q = 0; q < EW / 4; ++q) {
-        const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float tcv = ftanh(f4get(cc, j));
-          dct[4 * q + j] += dh[4 * q + j] * gov[4 * q + j] * (1.0f - tcv * tcv);
-        }
+      for (int j = 0; j < EW; ++j) {
+        const float tcv = ftanh(ccv[j]);
+        dct[j] += dh[j] * gov[j] * (1.0f - tcv * tcv);
       }
     }
     // ---- gate derivatives, gate by gate = k-block pair by k-block pair of the dgrad A operand -----------------
@@ -128,31 +120,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         for (int j = 0; j < EW; ++j)
           dz[j] = (g == 0) ? dct[j] * gu[j] * gi[j] * (1.0f - gi[j]) : dct[j] * gi[j] * (1.0f - gu[j] * gu[j]);
       } else if (g == 1) {
-        float gf[EW];
+        float gf[EW], cpv[EW], dcp[EW];
         ld_fm<EW>(gates_fm, 1 * NH + e0, B, b, gf);
+        ld_state<FM, EW>(k.c_prev, (size_t)i, b, e0, B, cpv);
 #pragma unroll
-        for (int q = 0; q < EW / 4; ++q) {
-          const float4 cp = *reinterpret_cast<const float4*>(k.c_prev + row * NH + e0 + 4 * q);
-          float dcp[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float fg = gf[4 * q + j];
-            dz[4 * q + j] = dct[4 * q + j] * (f4get(cp, j) * nd) * fg * (1.0f - fg);
-            dcp[j] = dct[4 * q + j] * fg * nd;
-          }
-          *reinterpret_cast<float4*>(k.dc_out + row * NH + e0 + 4 * q) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+        for (int j = 0; j < EW; ++j) {
+          dz[j] = dct[j] * (cpv[j] * nd) * gf[j] * (1.0f - gf[j]);
+          dcp[j] = dct[j] * gf[j] * nd;
         }
+        st_state<FM, EW>(k.dc_out, (size_t)i, b, e0, B, dcp);
       } else {
-        float go[EW];
+        float go[EW], ccv[EW];
         ld_fm<EW>(gates_fm, 2 * NH + e0, B, b, go);
+        ld_state<FM, EW>(k.c_cur, (size_t)i, b, e0, B, ccv);
 #pragma unroll
-        for (int q = 0; q < EW / 4; ++q) {
-          const float4 cc = *reinterpret_cast<const float4*>(k.c_cur + row * NH + e0 + 4 * q);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float og = go[4 * q + j], tcv = ftanh(f4get(cc, j));
-            dz[4 * q + j] = dh[4 * q + j] * tcv * og * (1.0f - og);
-          }
+        for (int j = 0; j < EW; ++j) {
+          const float tcv = ftanh(ccv[j]);
+          dz[j] = dh[j] * tcv * go[j] * (1.0f - go[j]);
         }
       }
       st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);
@@ -201,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       if (gp == NGRP - 1) {                    // own recurrent gradient, done-masked
 #pragma unroll
         for (int j = 0; j < EW; ++j) d[j] *= nd;
-        store_vec<EW>(k.dh_out + row * NH + e0, d);
+        st_state<FM, EW>(k.dh_out, (size_t)i, b, e0, B, d);
       } else if (VAR == NMARL_NC || VAR == NMARL_IA2C) {
         float sv[EW];
         ld_fm<EW>(sh_fm, gp * NH + e0, B, b, sv);
@@ -246,9 +230,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           const float nn = (float)ag.n_nbr;
 #pragma unroll
           for (int j = 0; j < EW; ++j) d[j] /= nn;
-          for (int s2 = 0; s2 < ag.n_nbr; ++s2) store_vec<EW>(k.dmsg_out + (((size_t)i * NMARL_MAX_NBR + s2) * B + b) * NH + e0, d);
+          for (int s2 = 0; s2 < ag.n_nbr; ++s2) st_state<FM, EW>(k.dmsg_out, (size_t)i * NMARL_MAX_NBR + s2, b, e0, B, d);
         } else {
-          store_vec<EW>(k.dmsg_out + (((size_t)i * NMARL_MAX_NBR + s) * B + b) * NH + e0, d);
+          st_state<FM, EW>(k.dmsg_out, (size_t)i * NMARL_MAX_NBR + s, b, e0, B, d);
         }
       }
       tc::fence_before_sync();
@@ -262,9 +246,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
   if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
 }
 
-template <int VAR>
-int launch_tc_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
-  auto kern = tc_cell_bwd_kernel<VAR>;
+template <int VAR, bool FM>
+int launch_tc_bwd_fm(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
+  auto kern = tc_cell_bwd_kernel<VAR, FM>;
   static bool configured = false;
   if (!configured) {
     NMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -274,6 +258,11 @@ int launch_tc_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   return 0;
+}
+
+template <int VAR>
+int launch_tc_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
+  return k.state_fm ? launch_tc_bwd_fm<VAR, true>(m, k, st) : launch_tc_bwd_fm<VAR, false>(m, k, st);
 }
 
 }  // namespace

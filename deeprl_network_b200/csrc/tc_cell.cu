@@ -27,7 +27,7 @@ namespace {
 
 using namespace tcrow;
 
-template <int VAR, int MODE>
+template <int VAR, int MODE, bool FM>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid_constant__ nmarl_model m,
                                                                     const __grid_constant__ FwdK k) {
   constexpr bool SAVE = (MODE == MODE_TRAIN || MODE == MODE_PS);   // store activations for BPTT
@@ -138,14 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
       for (int s = 0; s < NPRE; ++s) {
         if (s < ag.n_nbr) {
-          const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH + c0;
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb)
-#pragma unroll
-            for (int q = 0; q < W / 4; ++q) {
-              const float4 w = *reinterpret_cast<const float4*>(hp + hb * 32 + 4 * q);
-              mv[s][hb][4 * q] = w.x; mv[s][hb][4 * q + 1] = w.y; mv[s][hb][4 * q + 2] = w.z; mv[s][hb][4 * q + 3] = w.w;
-            }
+          for (int hb = 0; hb < 2; ++hb) ld_state<FM, W>(src, (size_t)ag.nbr[s], b, hb * 32 + c0, B, mv[s][hb]);
         }
       }
     }
@@ -156,12 +150,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < W; ++j) mv[0][hb][j] = 0.f;
         for (int s = 0; s < ag.n_nbr; ++s) {
-          const float* hp = a.h_in + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
+          float w8[W];
+          ld_state<FM, W>(a.h_in, (size_t)ag.nbr[s], b, hb * 32 + c0, B, w8);
 #pragma unroll
-          for (int q = 0; q < W / 4; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
-            mv[0][hb][4 * q] += w.x; mv[0][hb][4 * q + 1] += w.y; mv[0][hb][4 * q + 2] += w.z; mv[0][hb][4 * q + 3] += w.w;
-          }
+          for (int j = 0; j < W; ++j) mv[0][hb][j] += w8[j];
         }
 #pragma unroll
         for (int j = 0; j < W; ++j) mv[0][hb][j] /= nn;
@@ -170,12 +162,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     float hv[2][W];                                                       // own h, done-masked (utils.py:189-190)
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-      const float* hp = a.h_in + row * NH + hb * 32 + c0;
+      ld_state<FM, W>(a.h_in, (size_t)i, b, hb * 32 + c0, B, hv[hb]);
 #pragma unroll
-      for (int q = 0; q < W / 4; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
-        hv[hb][4 * q] = w.x * nd; hv[hb][4 * q + 1] = w.y * nd; hv[hb][4 * q + 2] = w.z * nd; hv[hb][4 * q + 3] = w.w * nd;
-      }
+      for (int j = 0; j < W; ++j) hv[hb][j] *= nd;
     }
     STAMP();
     // ---- encoder GEMMs: A chunks back to back, one completion wait ----------------------------------------------
@@ -202,12 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < W; ++j) t[j] = (s == 0) ? mv[0][hb][j] : mv[NPRE - 1][hb][j];
           } else {
-            const float* hp = src + ((size_t)ag.nbr[s] * B + b) * NH + hb * 32 + c0;
-#pragma unroll
-            for (int q = 0; q < W / 4; ++q) {
-              const float4 w = *reinterpret_cast<const float4*>(hp + 4 * q);
-              t[4 * q] = w.x; t[4 * q + 1] = w.y; t[4 * q + 2] = w.z; t[4 * q + 3] = w.w;
-            }
+            ld_state<FM, W>(src, (size_t)ag.nbr[s], b, hb * 32 + c0, B, t);
           }
           if (SAVE) st_fm<W>(xin_fm, xm0 + s * NH + hb * 32 + c0, B, b, t);
           produce_in(c, t);
@@ -286,10 +270,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       tc::tmem_ld8(tmem + c.lane_base + ACC_COL + 3 * NH + u0, gu);
       tc::wait_ld();
       STAMP();
-      float cn[8], hn[8];
+      float cn[8], hn[8], cpv[8];
+      ld_state<FM, 8>(a.c_in, (size_t)i, b, u0, B, cpv);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const float4 cp4 = *reinterpret_cast<const float4*>(a.c_in + row * NH + u0 + 4 * q);
         const float4 bi = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 0 * NH + u0) + q);
         const float4 bf = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 1 * NH + u0) + q);
         const float4 bo = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 2 * NH + u0) + q);
@@ -301,14 +285,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           gf[x] = fsigmoid(gf[x] + f4get(bf, j));
           go[x] = fsigmoid(go[x] + f4get(bo, j));
           gu[x] = ftanh(gu[x] + f4get(bu, j));
-          cn[x] = gf[x] * (f4get(cp4, j) * nd) + gi[x] * gu[x];
+          cn[x] = gf[x] * (cpv[x] * nd) + gi[x] * gu[x];
           hn[x] = go[x] * ftanh(cn[x]);
         }
       }
       STAMP();
       if (MODE != MODE_V) {
-        store_vec<8>(a.c_out + row * NH + u0, cn);
-        store_vec<8>(a.h_out + row * NH + u0, hn);
+        st_state<FM, 8>(a.c_out, (size_t)i, b, u0, B, cn);
+        st_state<FM, 8>(a.h_out, (size_t)i, b, u0, B, hn);
       }
       if (SAVE) {
         st_fm<8>(gates_fm, 0 * NH + u0, B, b, gi); st_fm<8>(gates_fm, 1 * NH + u0, B, b, gf);
@@ -441,7 +425,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       enc_wait(c);
       enc_load(c, ACC_COL, mo);
       bias_act(mo, P + ag.o_mfc_b + e0, 0);
-      store_vec<EW>(a.msg_out + row * NH + e0, mo);
+      st_state<FM, EW>(a.msg_out, (size_t)i, b, e0, B, mo);
     }
     STAMP();
     if (prof) prof[31] = pi_;
@@ -473,9 +457,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 }
 
 
-template <int VAR, int MODE>
-int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
-  auto kern = tc_cell_fwd_kernel<VAR, MODE>;
+template <int VAR, int MODE, bool FM>
+int launch_tc_fm(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
+  auto kern = tc_cell_fwd_kernel<VAR, MODE, FM>;
   static bool configured = false;
   if (!configured) {
     NMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -487,6 +471,11 @@ int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k2);
   NMARL_LAUNCH_CHECK();
   return 0;
+}
+
+template <int VAR, int MODE>
+int launch_tc(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
+  return k.a.state_fm ? launch_tc_fm<VAR, MODE, true>(m, k, st) : launch_tc_fm<VAR, MODE, false>(m, k, st);
 }
 
 template <int VAR>

@@ -108,6 +108,35 @@ __device__ __forceinline__ void ld_fm(const float* base, int f0, int B, int b, f
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] = base[(size_t)(f0 + j) * B + b];
 }
+// state tensors (h, c, messages and their gradients): plane p of [planes][B][64] (env-major, FM = false) or
+// [planes][64][B] (feature-major, FM = true: lane == env row -> one 128-byte line per warp access)
+template <bool FM, int NV>
+__device__ __forceinline__ void ld_state(const float* base, size_t plane, int b, int u0, int B, float (&v)[NV]) {
+  if (FM) {
+    const float* p = base + (plane * NH + u0) * (size_t)B + b;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = p[(size_t)j * B];
+  } else {
+    const float* p = base + (plane * (size_t)B + b) * NH + u0;
+#pragma unroll
+    for (int q = 0; q < NV / 4; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(p + 4 * q);
+      v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+  }
+}
+template <bool FM, int NV>
+__device__ __forceinline__ void st_state(float* base, size_t plane, int b, int u0, int B, const float (&v)[NV]) {
+  if (FM) {
+    float* p = base + (plane * NH + u0) * (size_t)B + b;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) p[(size_t)j * B] = v[j];
+  } else {
+    float* p = base + (plane * (size_t)B + b) * NH + u0;
+#pragma unroll
+    for (int q = 0; q < NV / 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
 template <int NV>
 __device__ __forceinline__ void store_vec(float* dst, const float (&s)[NV]) {
 #pragma unroll

@@ -448,7 +448,7 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ WgRedK k) {
 
 // heads: dW_pi = h^T dlogits, db_pi, dW_v = [h, onehot(a_nbr)]^T dv, db_v   (skinny; own kernel)
 struct HeadK {
-  int N, B, T, splits, n_a;
+  int N, B, T, splits, n_a, fm;
   const float* h1;           // h_seq + N*B*64  (h_t, t = 0..T-1)
   const float* dlv;          // [T][N][B][8]
   const int32_t* act;        // [T][N][B]
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __grid_constant__
   for (long r = r_begin + part; r < r_end; r += 4) {
     const long t = r / k.B, b = r - t * k.B;
     const size_t row = ((size_t)t * k.N + i) * k.B + b;
-    const float hv = k.h1[row * NH + u];
+    const float hv = k.fm ? k.h1[(((size_t)t * k.N + i) * NH + u) * k.B + b] : k.h1[row * NH + u];
     const float4 d0 = *reinterpret_cast<const float4*>(k.dlv + row * 8);
     const float4 d1 = *reinterpret_cast<const float4*>(k.dlv + row * 8 + 4);
     acc[0] = fmaf(hv, d0.x, acc[0]); acc[1] = fmaf(hv, d0.y, acc[1]); acc[2] = fmaf(hv, d0.z, acc[2]); acc[3] = fmaf(hv, d0.w, acc[3]);
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
 // Heads + A2C loss terms + d(loss)/d(logits, v) from the saved h sequence (thread == env row); used when the
 // rollout already saved the cell activations.  Same arithmetic as the TRAIN epilogue of the forward kernels.
 struct HeadFwdK {                 // pointers are for step 0; blockIdx.z = t strides them
-  int B, N, loss_tiles;
+  int B, N, loss_tiles, fm;
   const float* params; const float* h1; const int32_t* act; const float* Rs; const float* Advs;
   float* sv_dlv; float* loss_part;
   float loss_scale, v_coef, e_coef;
@@ -619,7 +619,13 @@ __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant_
     float v = 0.f;
 #pragma unroll 4
     for (int q = 0; q < NH / 4; ++q) {
-      const float4 h4 = *reinterpret_cast<const float4*>(k.h1 + row * NH + 4 * q);
+      float4 h4;
+      if (k.fm) {
+        const float* hp = k.h1 + ((tb / B + i) * NH + 4 * q) * (size_t)B + b;      // [t][agent][unit][env]
+        h4 = make_float4(hp[0], hp[(size_t)B], hp[2 * (size_t)B], hp[3 * (size_t)B]);
+      } else {
+        h4 = *reinterpret_cast<const float4*>(k.h1 + row * NH + 4 * q);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float hv = f4get(h4, j);
@@ -760,6 +766,8 @@ int check_bwd_args(const nmarl_model* m, const nmarl_bwd_args* a) {
   NMARL_CHECK(m->variant == NMARL_IA2C || a->dmsg, "a2c_backward: dmsg buffer required");
   NMARL_CHECK((m->variant != NMARL_IC3 && m->variant != NMARL_DIAL) || a->sv_enc, "a2c_backward: sv_enc required");
   NMARL_CHECK(m->variant != NMARL_DIAL || (a->msg_seq && a->sv_dmp), "a2c_backward: DIAL buffers required");
+  NMARL_CHECK(!a->state_fm || (m->variant != NMARL_DIAL && a->wpack != nullptr && a->B % 128 == 0),
+              "a2c_backward: feature-major state needs the tensor-core path (and is not implemented for DIAL)");
   NMARL_CHECK((m->variant != NMARL_NC && m->variant != NMARL_DIAL) || a->fp, "a2c_backward: fp required");
   return 0;
 }
@@ -812,7 +820,7 @@ extern "C" int nmarl_a2c_train_forward(const nmarl_model* m, const nmarl_bwd_arg
     f.c_out = a->c_seq + (size_t)(t + 1) * nb * NH; f.h_out = a->h_seq + (size_t)(t + 1) * nb * NH;
     if (m->variant == NMARL_DIAL) { f.msg_in = a->msg_seq + (size_t)t * nb * NH; f.msg_out = a->msg_seq + (size_t)(t + 1) * nb * NH; }
     f.act_in = a->act + (size_t)t * nb;
-    f.wpack = a->wpack; f.tc_err = a->tc_err;
+    f.wpack = a->wpack; f.tc_err = a->tc_err; f.state_fm = a->state_fm;
     int rc = nmarl_launch_train_fwd(m, &f, a->Rs + (size_t)t * nb, a->Advs + (size_t)t * nb,
                                     a->sv_xin + (size_t)t * nb * LDI, a->sv_sh + (size_t)t * nb * (m->s_dim + NH),
                                     a->sv_gates + (size_t)t * nb * NG, a->sv_enc ? a->sv_enc + (size_t)t * nb * 128 : nullptr,
@@ -830,7 +838,7 @@ extern "C" int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args*
   const size_t nb = (size_t)N * B;
   const int tiles = nmarl_fwd_tiles(B);
   HeadFwdK k{};
-  k.B = B; k.N = N; k.loss_tiles = tiles; k.params = a->params;
+  k.B = B; k.N = N; k.loss_tiles = tiles; k.params = a->params; k.fm = a->state_fm;
   k.h1 = a->h_seq + nb * NH;                                  // h after step t = h_seq[t + 1]
   k.act = a->act; k.Rs = a->Rs; k.Advs = a->Advs;
   k.sv_dlv = a->sv_dlv; k.loss_part = a->loss_part;
@@ -884,7 +892,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     }
     k.sv_dz = a->sv_dz + (size_t)t * nb * NG;
     k.sv_dpre = a->sv_dpre + (size_t)t * nb * 192;
-    k.wpack = a->wpack; k.tc_err = a->tc_err;
+    k.wpack = a->wpack; k.tc_err = a->tc_err; k.state_fm = a->state_fm;
     const bool use_tc = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
     k.dzT = (use_tc && a->sv_dzT) ? a->sv_dzT + (size_t)t * N * (B / 32) * (2 * 256 * 32) : nullptr;
     k.ndp = nmarl_tc_ndp(m);
@@ -940,7 +948,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   }
   {
     HeadK h{};
-    h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a;
+    h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a; h.fm = a->state_fm;
     h.h1 = a->h_seq + nb * NH; h.dlv = a->sv_dlv; h.act = a->act; h.ws = a->ws;
     NMARL_CHECK((int64_t)h.splits * N * HEAD_WS <= a->ws_floats, "head wgrad: workspace too small");
     head_wgrad_kernel<<<dim3(h.splits, N), 256, 0, st>>>(*m, h);

@@ -140,6 +140,7 @@ typedef struct {
   /* optional (p-call, tensor-core path only): save the activations BPTT needs while rolling out, so the
    * update can skip the separate training forward (same inputs, same weights => same numbers):         */
   float* sv_xin; float* sv_sh; float* sv_gates; float* sv_enc;   /* step-t slices, see nmarl_bwd_args      */
+  int32_t state_fm;        /* tensor-core path only: c/h/msg tensors are feature-major [N][64][B]   */
 } nmarl_fwd_args;
 
 int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
@@ -204,6 +205,8 @@ typedef struct {
                                 ndp = 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C).  On the tensor-core path (wpack set,
                                 B % 128 == 0) sv_xin / sv_sh / sv_gates / sv_enc / sv_dz are FEATURE-MAJOR
                                 [T][N][feature][B] and sv_dpre is unused.                                          */
+  int32_t state_fm;          /* tensor-core path only: h_seq / c_seq / msg_seq / dh_rec / dc_rec / dmsg are
+                                feature-major ([..][64][B] instead of [..][B][64])                                  */
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */
