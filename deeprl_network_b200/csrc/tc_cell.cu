@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
       STAMP();
       float cn[8], hn[8], cpv[8];
       ld_state<FM, 8>(a.c_in, (size_t)i, b, u0, B, cpv);
+      // MUFU budget: the SFU (16 lanes/clk/SM) bounds this loop, so reciprocals are shared pairwise:
+      // 1/(1+a), 1/(1+b) from ONE rcp of (1+a)(1+b)  ->  5 ex2 + 2.5 rcp per hidden unit instead of 5 + 5
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const float4 bi = __ldg(reinterpret_cast<const float4*>(P + ag.o_b + 0 * NH + u0) + q);
@@ -281,13 +283,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int x = 4 * q + j;
-          gi[x] = fsigmoid(gi[x] + f4get(bi, j));
-          gf[x] = fsigmoid(gf[x] + f4get(bf, j));
-          go[x] = fsigmoid(go[x] + f4get(bo, j));
-          gu[x] = ftanh(gu[x] + f4get(bu, j));
+          const float di = 1.0f + __expf(fminf(-(gi[x] + f4get(bi, j)), 40.0f));
+          const float df = 1.0f + __expf(fminf(-(gf[x] + f4get(bf, j)), 40.0f));
+          const float dO = 1.0f + __expf(fminf(-(go[x] + f4get(bo, j)), 40.0f));
+          const float du = 1.0f + __expf(fminf(-2.0f * (gu[x] + f4get(bu, j)), 40.0f));
+          const float r1 = frcp_(di * df), r2 = frcp_(dO * du);
+          gi[x] = r1 * df;                          // sigmoid(i)
+          gf[x] = r1 * di;                          // sigmoid(f)
+          go[x] = r2 * du;                          // sigmoid(o)
+          gu[x] = fmaf(2.0f, r2 * dO, -1.0f);       // tanh(u)
           cn[x] = gf[x] * (cpv[x] * nd) + gi[x] * gu[x];
-          hn[x] = go[x] * ftanh(cn[x]);
         }
+      }
+#pragma unroll
+      for (int x = 0; x < 8; x += 2) {              // tanh(c) for two units from one reciprocal
+        const float d0 = 1.0f + __expf(fminf(-2.0f * cn[x], 40.0f)), d1 = 1.0f + __expf(fminf(-2.0f * cn[x + 1], 40.0f));
+        const float r = frcp_(d0 * d1);
+        hn[x] = go[x] * fmaf(2.0f, r * d1, -1.0f);
+        hn[x + 1] = go[x + 1] * fmaf(2.0f, r * d0, -1.0f);
       }
       STAMP();
       if (MODE != MODE_V) {

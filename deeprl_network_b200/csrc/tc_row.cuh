@@ -153,8 +153,13 @@ __device__ __forceinline__ void bias_act(float (&v)[EW], const float* __restrict
 }
 // MUFU-based activations for the tensor-core epilogues (ex2.approx + rcp): absolute error ~1e-7, well inside the
 // 1e-5 parity budget, ~6x fewer instructions than expf/tanhf + IEEE division.
-__device__ __forceinline__ float fsigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return fmaf(2.0f, __frcp_rn(1.0f + __expf(-2.0f * x)), -1.0f); }
+__device__ __forceinline__ float frcp_(float x) {          // one MUFU.RCP (1 ulp), no IEEE fix-up path
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fsigmoid(float x) { return frcp_(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return fmaf(2.0f, frcp_(1.0f + __expf(-2.0f * x)), -1.0f); }
 __device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory"); }
 
 

@@ -189,6 +189,8 @@ class CACCEnv:
         self.t = 0
         self.fp = np.ones((self.n_agent, self.n_a)) / self.n_a
         self.rewards = [0]
+        if self.is_record:                       # the traffic log starts with the reset state (cacc_env.py:183-188)
+            self._trace = [torch.stack([self.hs[:, 0], self.vs[:, 0], self.us[:, 0]]).cpu().numpy()]
         return self._host_obs()
 
     def step(self, action):
@@ -241,10 +243,7 @@ class CACCEnv:
             self._trace = []
 
     def _record_step(self):
-        st = torch.stack([self.hs[:, 0], self.vs[:, 0], self.us[:, 0]]).cpu().numpy()
-        if self.t == 1:
-            self._trace = []
-        self._trace.append(st)
+        self._trace.append(torch.stack([self.hs[:, 0], self.vs[:, 0], self.us[:, 0]]).cpu().numpy())
 
     def _log_control_data(self, action, global_reward):
         self.control_data.append({'episode': self.cur_episode, 'time_sec': self.t * self.dt, 'step': self.t,
@@ -256,8 +255,8 @@ class CACCEnv:
         hs, vs, us = tr[:, 0], tr[:, 1], tr[:, 2]
         df = pd.DataFrame()
         df['episode'] = np.ones(len(hs)) * self.cur_episode
-        df['time_sec'] = (np.arange(len(hs)) + 1) * self.dt
-        df['reward'] = np.array(self.rewards[1:])
+        df['time_sec'] = np.arange(len(hs)) * self.dt
+        df['reward'] = np.array(self.rewards)
         df['lead_headway_m'] = hs[:, 0]
         df['avg_headway_m'] = np.mean(hs[:, 1:], axis=1)
         df['std_headway_m'] = np.std(hs[:, 1:], axis=1)

@@ -147,6 +147,24 @@ def buffer_case(au, alpha, multi=True, T=60, n=8, seed=0):
     return out
 
 
+def eval_case(CACCEnv, ini, kind, out_prefix):
+    """Evaluator-style recorded test episode (utils.py:321-336 + cacc_env.py:81-137): the reference's own CSVs."""
+    cp = _cfg(ini)
+    env = CACCEnv(cp['ENV_CONFIG'])
+    env.init_test_seeds([2000])
+    env.train_mode = False
+    env.cur_episode = 0
+    env.init_data(True, False, out_prefix)
+    env.reset(test_ind=0)
+    acts = _actions(kind, env.T, env.n_agent)
+    for t in range(env.T):
+        _, _, d, _ = env.step(acts[t])
+        if d:
+            break
+    env.output_data()
+    return acts[:t + 1]
+
+
 def scheduler_case(au):
     s1 = au.Scheduler(5e-4, decay='constant')
     s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
@@ -193,6 +211,9 @@ def main():
     _, _, _, _, Rs, Advs = buf.sample_transition(R_end)
     print('KAT alpha=-1: Rs[0,:3]', Rs[0, :3], 'Advs[7,-2:]', Advs[7, -2:], 'sumRs', Rs.sum())
     np.savez_compressed(os.path.join(HERE, 'scheduler.npz'), **scheduler_case(au))
+    acts = eval_case(CACCEnv, 'config_ma2c_nc_catchup.ini', 'cyc', os.path.join(HERE, 'eval_'))
+    np.save(os.path.join(HERE, 'eval_actions.npy'), acts)
+    print('eval csvs', [f for f in os.listdir(HERE) if f.startswith('eval_')])
 
 
 if __name__ == '__main__':

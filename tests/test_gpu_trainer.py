@@ -40,13 +40,14 @@ class Rec:
         return self.m.backward(R, *a, **k)
 
 
-@pytest.mark.parametrize('agent', ['ma2c_nc', 'ia2c', 'ma2c_ic3', 'ma2c_dial'])
-def test_trainer_lockstep_with_oracle(agent):
+@pytest.mark.parametrize('agent,cfg', [('ma2c_nc', None), ('ia2c', None), ('ma2c_ic3', None), ('ma2c_dial', None),
+                                       ('ia2c', 'config_ia2c_slowdown.ini')])       # last: spatial returns, per-agent rewards
+def test_trainer_lockstep_with_oracle(agent, cfg):
     from deeprl_network_b200.agents.models import IA2C, MA2C_DIAL, MA2C_IC3, MA2C_NC
     from deeprl_network_b200.envs.cacc_env import CACCEnv
     from deeprl_network_b200.utils import Counter, Trainer
     cls = {'ma2c_nc': MA2C_NC, 'ia2c': IA2C, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}[agent]
-    cp = load_cfg(CFG[agent])
+    cp = load_cfg(cfg or CFG[agent])
     # CUDA side (weights drawn from np.random right after the env seeds it -- reference order)
     env = CACCEnv(cp['ENV_CONFIG'])
     model = cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma, 1000,
@@ -93,3 +94,34 @@ def test_save_load_roundtrip(tmp_path):
     ob = env.reset()
     p1 = m.forward(ob, True, env.get_fingerprint()); p2 = m2.forward(ob, True, env.get_fingerprint())
     np.testing.assert_array_equal(p1, p2)
+
+
+def test_evaluator_csv_matches_reference(tmp_path):
+    """a recorded test episode writes the reference's two CSV files column for column
+    (fixtures produced by the unmodified reference env, tests/golden/make_golden.py)."""
+    import pandas as pd
+    from helpers import GOLDEN
+    from deeprl_network_b200.envs.cacc_env import CACCEnv
+    cp = load_cfg(CFG['ma2c_nc'])
+    env = CACCEnv(cp['ENV_CONFIG'])
+    env.init_test_seeds([2000])
+    env.train_mode = False
+    env.cur_episode = 0
+    out = str(tmp_path) + '/'
+    env.init_data(True, False, out)
+    env.reset(test_ind=0)
+    acts = np.load(GOLDEN + '/eval_actions.npy')
+    for t in range(len(acts)):
+        _, _, d, _ = env.step(acts[t])
+    assert d
+    env.output_data()
+    for kind in ('control', 'traffic'):
+        mine = pd.read_csv(out + 'catchup_ma2c_nc_%s.csv' % kind)
+        ref = pd.read_csv(GOLDEN + '/eval_catchup_ma2c_nc_%s.csv' % kind)
+        assert list(mine.columns) == list(ref.columns)
+        assert len(mine) == len(ref)
+        for col in ref.columns:
+            if ref[col].dtype == object:
+                assert (mine[col] == ref[col]).all(), col
+            else:
+                np.testing.assert_allclose(mine[col].values, ref[col].values, rtol=1e-9, atol=1e-9, err_msg=col)
