@@ -121,7 +121,7 @@ def test_evaluator_csv_matches_reference(tmp_path):
         assert list(mine.columns) == list(ref.columns)
         assert len(mine) == len(ref)
         for col in ref.columns:
-            if ref[col].dtype == object:
+            if not pd.api.types.is_numeric_dtype(ref[col]):
                 assert (mine[col] == ref[col]).all(), col
             else:
                 np.testing.assert_allclose(mine[col].values, ref[col].values, rtol=1e-9, atol=1e-9, err_msg=col)
