@@ -89,6 +89,9 @@ class PolicyEngine:
         self._train_ready = False
         self.saved_rollout = False
         self.fuse_save = os.environ.get('NMARL_NO_FUSE_SAVE', '0') != '1'
+        # v-calls run on a second stream: v(t) only feeds val_buf, so it overlaps env.step(t) and p(t+1)
+        self.overlap_v = os.environ.get('NMARL_NO_OVERLAP', '0') != '1'
+        self._vstream = None
         self.T_cur = T
         self.launches = 0
         self.repack()
@@ -240,18 +243,35 @@ class PolicyEngine:
         self.h_seq[0].copy_(self.h[self.cur]); self.c_seq[0].copy_(self.c[self.cur])
         if self.msg_seq is not None:
             self.msg_seq[0].copy_(self.msg[self.cur])
+        main = torch.cuda.current_stream()
+        if self.overlap_v and self._vstream is None:
+            self._vstream = torch.cuda.Stream(device=self.device)
+        side = self._vstream if self.overlap_v else None
+
+        def v_call(t, obs, fp, done, act, v):
+            # Reads obs/fp/done[t], act and state slot t+1; writes only v.  Nothing downstream in the rollout
+            # reads v, so on the second stream it fills the SMs the 256-CTA p-call / env step leave idle.
+            if side is None:
+                self._seq_call(t, obs, fp, done, 'v', act=act, v=v)
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._seq_call(t, obs, fp, done, 'v', act=act, v=v)
+
         for t in range(T):
             obs, fp, done = self.obs_buf[t], self.fp_buf[t], self.done_buf[t]
             self._seq_call(t, obs, fp, done, 'p', pi=self.fp_buf[t + 1], action=self.act_buf[t], mode=mode,
                            uniforms=None if uniforms is None else uniforms[t], save=True)
-            self._seq_call(t, obs, fp, done, 'v', act=self.act_buf[t], v=self.val_buf[t])
+            v_call(t, obs, fp, done, self.act_buf[t], self.val_buf[t])
             env.step_device(self.act_buf[t], obs_out=self.obs_buf[t + 1], reward_out=self.rew_buf[t],
                             greward_out=self.grew_buf[t], done_out=self.done_buf[t + 1])
             self.launches += 1
         # bootstrap (Q2): one more p-call (state advanced into slot T+1, not saved for BPTT) + v-call
         self._seq_call(T, self.obs_buf[T], self.fp_buf[T], self.done_buf[T], 'p', pi=self.boot_pi, action=self.boot_act,
                        mode=mode, uniforms=None if uniforms is None else uniforms[T])
-        self._seq_call(T, self.obs_buf[T], self.fp_buf[T], self.done_buf[T], 'v', act=self.boot_act, v=self.R_end)
+        v_call(T, self.obs_buf[T], self.fp_buf[T], self.done_buf[T], self.boot_act, self.R_end)
+        if side is not None:
+            main.wait_stream(side)
         self.h[self.cur].copy_(self.h_seq[T + 1]); self.c[self.cur].copy_(self.c_seq[T + 1])
         if self.msg_seq is not None:
             self.msg[self.cur].copy_(self.msg_seq[T + 1])

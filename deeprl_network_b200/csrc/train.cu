@@ -871,6 +871,30 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
       transpose_kernel<<<dim3(2, 2), blk, 0, st>>>(a->params + ag.o_mfc_w, a->wt + ag.t_mfc, NH, NH);
   }
   NMARL_LAUNCH_CHECK();
+  // 1b. policy/value head weight gradients need only sv_dlv and h_seq: they run on a forked stream
+  //     beside the BPTT chain (whose 256-CTA launches leave SMs idle in their second wave) and join
+  //     before the weight-gradient phase, which shares the workspace.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    NMARL_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    NMARL_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    NMARL_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  NMARL_CUDA(cudaEventRecord(ev_fork, st));
+  NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  {
+    HeadK h{};
+    h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a; h.fm = a->state_fm;
+    h.h1 = a->h_seq + nb * NH; h.dlv = a->sv_dlv; h.act = a->act; h.ws = a->ws;
+    NMARL_CHECK((int64_t)h.splits * N * HEAD_WS <= a->ws_floats, "head wgrad: workspace too small");
+    head_wgrad_kernel<<<dim3(h.splits, N), 256, 0, side>>>(*m, h);
+    NMARL_LAUNCH_CHECK();
+    HeadRedK r{N, h.splits, m->n_a, a->ws, a->grads};
+    head_reduce_kernel<<<N, 256, 0, side>>>(*m, r);
+    NMARL_LAUNCH_CHECK();
+  }
+  NMARL_CUDA(cudaEventRecord(ev_join, side));
   // 2. reverse time
   for (int t = T - 1; t >= 0; --t) {
     BwdK k{};
@@ -916,6 +940,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     }
   }
   // 3. weight gradients
+  NMARL_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   int Ka[NMARL_MAX_AGENT], ow[NMARL_MAX_AGENT], ob[NMARL_MAX_AGENT];
   const int LDI = m->kx_pad + m->kp_pad + m->km_pad;
   const bool tc_wg = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
@@ -946,17 +971,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     for (int i = 0; i < N; ++i) { Ka[i] = NH; ow[i] = m->agent[i].o_mfc_w; ob[i] = m->agent[i].o_mfc_b; }
     if (run_wgrad(m, a, 1, a->h_seq, NH, 0, a->sv_dmp, NH, 0, Ka, ow, ob, st)) return 1;
   }
-  {
-    HeadK h{};
-    h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a; h.fm = a->state_fm;
-    h.h1 = a->h_seq + nb * NH; h.dlv = a->sv_dlv; h.act = a->act; h.ws = a->ws;
-    NMARL_CHECK((int64_t)h.splits * N * HEAD_WS <= a->ws_floats, "head wgrad: workspace too small");
-    head_wgrad_kernel<<<dim3(h.splits, N), 256, 0, st>>>(*m, h);
-    NMARL_LAUNCH_CHECK();
-    HeadRedK r{N, h.splits, m->n_a, a->ws, a->grads};
-    head_reduce_kernel<<<N, 256, 0, st>>>(*m, r);
-    NMARL_LAUNCH_CHECK();
-  }
+  (void)0;
   return 0;
 }
 
