@@ -167,13 +167,14 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from deeprl_network_b200 import _lib as L
-    from deeprl_network_b200.agents.models import MA2C_NC, MA2C_IC3, MA2C_DIAL, IA2C
+    from deeprl_network_b200.agents.models import MA2C_NC, MA2C_IC3, MA2C_DIAL, IA2C, IA2C_FP, IA2C_CU
     from deeprl_network_b200.envs.cacc_env import CACCEnv
     from deeprl_network_b200.utils import VecTrainer
     B = args.n_env
     cp = load_cfg(args.config, n_env=B, seed=12 + 1000 * rank)
     env = CACCEnv(cp['ENV_CONFIG'])
-    cls = {'ma2c_nc': MA2C_NC, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL, 'ia2c': IA2C}[env.agent]
+    cls = {'ma2c_nc': MA2C_NC, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL, 'ia2c': IA2C, 'ia2c_fp': IA2C_FP,
+           'ma2c_cu': IA2C_CU}[env.agent]
     np.random.seed(12)                                   # identical initial weights on every rank
     kw = dict(obs_mode='gather') if env.agent == 'ia2c' else {}
     model = cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma, 10 ** 9,

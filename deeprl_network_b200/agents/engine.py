@@ -33,7 +33,9 @@ class PolicyEngine:
         self.world = torch.distributed.get_world_size(group) if (group is not None or (
             torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
         self.model = layout.c_model()
-        self.variant = layout.variant
+        # kernel family: ma2c_cu runs the IA2C cell, ia2c_fp the NeurComm cell (layout.py docstring)
+        self.agent_name = layout.variant
+        self.variant = {'ma2c_cu': 'ia2c', 'ia2c_fp': 'ma2c_nc'}.get(layout.variant, layout.variant)
         dev, N, B, T = self.device, self.N, self.B, self.T
         f32 = dict(dtype=torch.float32, device=dev)
         if flat_params is None:
@@ -74,7 +76,7 @@ class PolicyEngine:
         self.Rs, self.Advs = torch.zeros(T, N, B, **f32), torch.zeros(T, N, B, **f32)
         self.pi_tmp = torch.zeros(N, B, self.n_a, **f32)
         self.lr_dev = torch.zeros(1, **f32)
-        self.n_groups = N if self.variant == 'ia2c' else 1
+        self.n_groups = N if self.model.per_agent_norm else 1
         self.norm_out = torch.zeros(self.n_groups, **f32)
         self.opt_scratch = torch.zeros(1024, **f32)
         self.rng = torch.tensor([int(rng_seed) & (2 ** 63 - 1), 0], dtype=torch.int64, device=dev)
@@ -378,6 +380,13 @@ class PolicyEngine:
                                                 float(h['epsilon']), L.ptr(self.norm_out), L.ptr(self.opt_scratch),
                                                 L.stream()), 'nmarl_clip_rmsprop_step')
         self.launches += 2
+        if self.agent_name == 'ma2c_cu':     # ConsensusPolicy.backward: sess.run(_consensus_update) after the optimizer
+            if getattr(self, '_cu_scratch', None) is None:
+                self._cu_scratch = torch.zeros(self.N * ((self.layout.s_dim + NH) * 4 * NH + 4 * NH),
+                                               dtype=torch.float32, device=self.device)
+            L.check(L.lib().nmarl_consensus_update(C.byref(self.model), L.ptr(self.params), L.ptr(self._cu_scratch),
+                                                   L.stream()), 'nmarl_consensus_update')
+            self.launches += 2
         self.c_bw.copy_(self.c[self.cur]); self.h_bw.copy_(self.h[self.cur])
         self.repack()
         self._refresh_msg()        # DIAL: cached sender-side messages depend on the updated w_mfc

@@ -51,6 +51,8 @@ class IA2C:
         self.sess = None
         if obs_mode is None:
             obs_mode = 'concat' if self.variant == 'ia2c' else 'gather'
+        if self.variant == 'ia2c_fp':     # "neighborhood policies are included in local state" (agents/models.py:172-177)
+            self.n_s_ls = [n + self.n_a * int(np.sum(self.neighbor_mask[i])) for i, n in enumerate(self.n_s_ls)]
         self.layout = ModelLayout(self.variant, self.n_s_ls, self.n_a, self.neighbor_mask,
                                   n_h=self.n_lstm, n_fc=self.n_fc, obs_mode=obs_mode)
         self.nbr = self.layout.nbr
@@ -102,9 +104,11 @@ class IA2C:
     def forward(self, obs, done, nactions=None, out_type='p'):
         """agents/models.py:44-51 -> list of N arrays (pi_i) or N scalars (v_i)."""
         e, s = self.engine, self._one
-        self._upload_step(obs, done, None)
+        ps = self._ps_from_obs(obs)
+        self._upload_step(obs, done, ps)
+        fp = None if ps is None else s['fp']
         if out_type.startswith('p'):
-            e.step_p(s['obs'], None, s['done'], e.pi_tmp)
+            e.step_p(s['obs'], fp, s['done'], e.pi_tmp)
             pi = e.pi_tmp[:, 0].cpu().numpy()
             return [pi[i] for i in range(self.n_agent)]
         a = np.zeros(self.n_agent, dtype=np.int32)
@@ -112,13 +116,17 @@ class IA2C:
             for k, j in enumerate(self.nbr[i]):
                 a[j] = int(nactions[i][k])
         s['act'].copy_(torch.from_numpy(a)[:, None])
-        e.step_v(s['obs'], None, s['done'], s['act'], s['v'])
+        e.step_v(s['obs'], fp, s['done'], s['act'], s['v'])
         v = s['v'][:, 0].cpu().numpy()
         return [v[i] for i in range(self.n_agent)]
 
+    def _ps_from_obs(self, obs):
+        """Fingerprints carried inside the observation (only IA2C_FP has them)."""
+        return None
+
     def add_transition(self, ob, naction, action, reward, value, done):
         """agents/models.py:26-32 (reward norm/clip happen inside the returns kernel)."""
-        self._obs.append(self._pack_obs(ob)); self._ps.append(None); self._acts.append(np.asarray(action, dtype=np.int32))
+        self._obs.append(self._pack_obs(ob)); self._ps.append(self._ps_from_obs(ob)); self._acts.append(np.asarray(action, dtype=np.int32))
         self._rs.append(reward); self._vs.append(np.asarray(value, dtype=np.float32)); self._dones.append(bool(done))
 
     def backward(self, Rends, dt=0, summary_writer=None, global_step=None):
@@ -145,9 +153,10 @@ class IA2C:
         """Scalar tags of agents/policies.py:41-47 / 266-273."""
         ls = self.engine.losses()
         norms = self.engine.norm_out.cpu().numpy()
-        names = ['lstm_%d' % i for i in range(self.n_agent)] if self.variant == 'ia2c' else [self.layout_scope()]
-        for k, name in enumerate(names[:1] if self.variant == 'ia2c' else names):
-            sel = slice(k, k + 1) if self.variant == 'ia2c' else slice(None)
+        per_agent = bool(self.engine.model.per_agent_norm)
+        names = ['lstm_%d' % i for i in range(self.n_agent)] if per_agent else [self.layout_scope()]
+        for k, name in enumerate(names[:1] if per_agent else names):
+            sel = slice(k, k + 1) if per_agent else slice(None)
             pl, vl, el = ls['policy_loss'][sel].sum(), ls['value_loss'][sel].sum(), ls['entropy_loss'][sel].sum()
             writer.add_scalar('loss/%s_entropy_loss' % name, el, global_step)
             writer.add_scalar('loss/%s_policy_loss' % name, pl, global_step)
@@ -157,7 +166,7 @@ class IA2C:
             writer.add_scalar('train/%s_gradnorm' % name, float(norms[k]), global_step)
 
     def layout_scope(self):
-        return {'ma2c_nc': 'nc', 'ma2c_ic3': 'ic3', 'ma2c_dial': 'dial'}.get(self.variant, 'lstm')
+        return {'ma2c_nc': 'nc', 'ma2c_ic3': 'ic3', 'ma2c_dial': 'dial', 'ma2c_cu': 'cu'}.get(self.variant, 'lstm')
 
     def reset(self):
         self.engine.reset_states()
@@ -210,6 +219,24 @@ class IA2C:
         self.engine.update(self.lr_scheduler.get(self.n_step))
 
 
+class IA2C_FP(IA2C):
+    """Fingerprint IA2C (agents/models.py:161-188): FPPolicy encodes the neighbours' last policies, which the
+    environment appends to each observation (envs/cacc_env.py:74-77), with a second fc layer.  The kernels
+    gather observations and fingerprints per neighbour on the device, so the host splits the reference's
+    concatenated observation back into own features and one policy row per agent."""
+    variant = 'ia2c_fp'
+
+    def _ps_from_obs(self, obs):
+        ps = np.full((self.n_agent, self.n_a), 1.0 / self.n_a, dtype=np.float32)
+        b = self.layout.base_n_s
+        for i in range(self.n_agent):
+            o = np.asarray(obs[i], dtype=np.float32).ravel()
+            n_x = b * (1 + len(self.nbr[i]))
+            for k, j in enumerate(self.nbr[i]):
+                ps[j] = o[n_x + k * self.n_a: n_x + (k + 1) * self.n_a]
+        return ps
+
+
 class MA2C_NC(IA2C):
     """NeurComm (agents/models.py:191-258): centralised graph over all agents."""
     variant = 'ma2c_nc'
@@ -240,3 +267,10 @@ class MA2C_IC3(MA2C_NC):
 class MA2C_DIAL(MA2C_NC):
     """DIAL (agents/models.py:295-309)."""
     variant = 'ma2c_dial'
+
+
+class IA2C_CU(MA2C_NC):
+    """Consensus update (agents/models.py:261-275, config key ``ma2c_cu``): per-agent fc + LSTM on the agent's
+    own observation inside one graph (one loss, one global clip); after every optimizer step each agent's
+    LSTM weights are replaced by the mean over itself and its neighbours (nmarl_consensus_update)."""
+    variant = 'ma2c_cu'

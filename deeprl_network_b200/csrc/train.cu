@@ -1002,3 +1002,37 @@ extern "C" int nmarl_clip_rmsprop_step(const nmarl_model* m, float* params, floa
   NMARL_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- consensus update of the LSTM blocks (ma2c_cu) -------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) consensus_mean_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ params,
+                                                            float* __restrict__ scratch, int n) {
+  const int i = blockIdx.y;
+  const nmarl_agent& ag = m.agent[i];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    float s = params[ag.o_wxh + e];                      // own block first, then neighbours ascending
+    for (int k = 0; k < ag.n_nbr; ++k) s += params[m.agent[ag.nbr[k]].o_wxh + e];
+    scratch[(size_t)i * n + e] = s / (float)(1 + ag.n_nbr);
+  }
+}
+__global__ void __launch_bounds__(256) consensus_store_kernel(const __grid_constant__ nmarl_model m, float* __restrict__ params,
+                                                             const float* __restrict__ scratch, int n) {
+  const int i = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    params[m.agent[i].o_wxh + e] = scratch[(size_t)i * n + e];
+}
+}  // namespace
+
+extern "C" int nmarl_consensus_update(const nmarl_model* m, float* params, float* scratch, void* stream) {
+  if (nmarl_check_model(m)) return 1;
+  NMARL_CHECK(params && scratch, "consensus_update: missing buffers");
+  const int n = (m->s_dim + NH) * NG + NG;
+  for (int i = 0; i < m->n_agent; ++i)
+    NMARL_CHECK(m->agent[i].o_b == m->agent[i].o_wxh + (m->s_dim + NH) * NG, "consensus_update: LSTM block of agent %d is not contiguous", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  consensus_mean_kernel<<<dim3(32, m->n_agent), 256, 0, st>>>(*m, params, scratch, n);
+  NMARL_LAUNCH_CHECK();
+  consensus_store_kernel<<<dim3(32, m->n_agent), 256, 0, st>>>(*m, params, scratch, n);
+  NMARL_LAUNCH_CHECK();
+  return 0;
+}

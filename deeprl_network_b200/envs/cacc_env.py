@@ -163,7 +163,9 @@ class CACCEnv:
         base = self.obs_dev[:, 0, :5].double().cpu().numpy()
         if not self.agent.startswith('ia2c'):
             return [base[i] for i in range(self.n_agent)]
-        return [np.concatenate([base[i]] + [base[j] for j in self.nbr[i]]) for i in range(self.n_agent)]
+        # ia2c_fp: neighbour fingerprints are attached at the end of the state array (cacc_env.py:74-77)
+        fps = (lambda i: [np.asarray(self.fp[j], dtype=np.float64) for j in self.nbr[i]]) if self.agent == 'ia2c_fp' else (lambda i: [])
+        return [np.concatenate([base[i]] + [base[j] for j in self.nbr[i]] + fps(i)) for i in range(self.n_agent)]
 
     def reset(self, gui=False, test_ind=-1):
         """envs/cacc_env.py:166-189: seed selection, np.random.seed, ``seed += 1`` on every reset;

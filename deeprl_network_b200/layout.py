@@ -6,7 +6,17 @@ parity tests can address weights by the reference's own names:
   CommNet   ic3/lstm_ic3_i/{w_msg,b_msg,w_ob,b_ob,wx_hid,wh_hid,b_hid}           agents/utils.py:361-377
   DIAL      dial/lstm_comm_i/{...}, dial/mfc_i/{w,b}                               agents/utils.py:535-566
   IA2C      lstm_i/fc/{w,b}, lstm_i/lstm/{wx,wh,b}                                 agents/policies.py:145-146
+  IA2C_FP   lstm_i/fcs/{w,b}, lstm_i/fcp/{w,b}, lstm_i/lstm/{wx,wh,b}              agents/policies.py:157-185
+  IA2C_CU   cu/fc_ia/{w,b}, cu/lstm_ia/{wx,wh,b}, cu/pi_i, cu/v_ia                 agents/policies.py:366-399
   heads     <scope>/pi_i/{w,b}, <scope>/v_i/{w,b}   (IA2C: lstm_i/pi, lstm_i/v)    agents/policies.py:50-77
+
+Two agents reuse another agent's kernels:
+  ma2c_cu  runs the IA2C cell with the agent's OWN observation only (ob[i], n_s = 5) and one global clip.
+  ia2c_fp  runs the NeurComm cell with a null message encoder: its [fcs | fcp] -> lstm network is the
+           NeurComm cell whose w_msg / b_msg and wx_hid rows 128..191 are zero.  relu(0) = 0 feeds exact
+           zeros into the gate GEMM and receives exact-zero gradients, so the padding never moves and
+           the outputs equal FPPolicy's bit for bit.  The padding has no reference name and is not part
+           of pack()/unpack()/checkpoints.
 
 In the flat buffer every tensor starts on a 16-byte boundary, one agent's tensors are
 contiguous (IA2C clips/optimises per agent) and wx_hid/wh_hid are adjacent so the LSTM gate
@@ -16,7 +26,8 @@ import numpy as np
 
 from . import _lib as L
 
-VARIANT_ID = {'ia2c': L.IA2C, 'ma2c_nc': L.NC, 'ma2c_ic3': L.IC3, 'ma2c_dial': L.DIAL}
+VARIANT_ID = {'ia2c': L.IA2C, 'ma2c_nc': L.NC, 'ma2c_ic3': L.IC3, 'ma2c_dial': L.DIAL, 'ma2c_cu': L.IA2C, 'ia2c_fp': L.NC}
+PER_AGENT_OPT = ('ia2c', 'ia2c_fp')        # one loss / clip / optimizer per agent (agents/models.py:34-42)
 SCOPE = {'ma2c_nc': 'nc', 'ma2c_ic3': 'ic3', 'ma2c_dial': 'dial'}
 CELL = {'ma2c_nc': 'lstm_comm', 'ma2c_ic3': 'lstm_ic3', 'ma2c_dial': 'lstm_comm'}
 NH = L.NH
@@ -43,7 +54,7 @@ class ModelLayout:
         if n_h != NH or n_fc != NH:
             raise ValueError('kernels are specialised for num_lstm = num_fc = 64 (got %d/%d)' % (n_h, n_fc))
         if variant not in VARIANT_ID:
-            raise ValueError('unsupported agent %r (hot path covers ia2c, ma2c_nc, ma2c_ic3, ma2c_dial)' % variant)
+            raise ValueError('unsupported agent %r (covered: ia2c, ia2c_fp, ma2c_cu, ma2c_nc, ma2c_ic3, ma2c_dial)' % variant)
         self.variant, self.vid = variant, VARIANT_ID[variant]
         mask = np.asarray(neighbor_mask).astype(int)
         N = len(mask)
@@ -57,7 +68,13 @@ class ModelLayout:
             raise ValueError('more than %d neighbours' % L.MAX_NBR)
         self.n_s_ls = [int(x) for x in n_s_ls]
         self.obs_mode = obs_mode
-        if variant == 'ia2c':
+        if variant == 'ia2c_fp':
+            # n_s_ls counts own + neighbour observations + neighbour fingerprints (agents/models.py:175)
+            assert obs_mode == 'gather', 'ia2c_fp observations are gathered on the device'
+            self.base_n_s = int(base_n_s) if base_n_s else (self.n_s_ls[0] - n_a * len(self.nbr[0])) // (1 + len(self.nbr[0]))
+            for i in range(N):
+                assert self.n_s_ls[i] == (self.base_n_s + n_a) * len(self.nbr[i]) + self.base_n_s, 'ia2c_fp n_s_ls'
+        elif variant == 'ia2c':
             if obs_mode == 'gather':
                 self.base_n_s = int(base_n_s) if base_n_s else self.n_s_ls[0] // (1 + len(self.nbr[0]))
                 for i in range(N):
@@ -67,13 +84,15 @@ class ModelLayout:
         else:
             self.base_n_s = self.n_s_ls[0]
             assert all(x == self.base_n_s for x in self.n_s_ls), 'MA2C agents must share n_s'
-        self.s_dim = 3 * NH if variant == 'ma2c_nc' else NH
+        self.s_dim = 3 * NH if variant in ('ma2c_nc', 'ia2c_fp') else NH
         self._build()
 
     # ------------------------------------------------------------------------------------------
     def _kx(self, i):
         if self.variant == 'ia2c' and self.obs_mode == 'concat':
             return self.n_s_ls[i]
+        if self.variant == 'ma2c_cu':
+            return self.base_n_s
         return self.base_n_s * (1 + len(self.nbr[i]))
 
     def _build(self):
@@ -91,6 +110,12 @@ class ModelLayout:
             off = _up4(off + int(np.prod(shape)))
             return o
 
+        def skip(n):                # unnamed zero padding (see the module docstring)
+            nonlocal off
+            o = off
+            off = _up4(off + int(n))
+            return o
+
         for i in range(N):
             nm = len(self.nbr[i])
             a = dict(p_begin=off)
@@ -106,6 +131,23 @@ class ModelLayout:
                 o2 = put(s + '/lstm/wh', (NH, 4 * NH)); assert o2 == a['o_wxh'] + NH * 4 * NH
                 a['o_b'] = put(s + '/lstm/b', (4 * NH,))
                 hp, hv = s + '/pi', s + '/v'
+            elif v == 'ma2c_cu':
+                a['o_w_ob'] = put('cu/fc_%da/w' % i, (kx, NH)); a['o_b_ob'] = put('cu/fc_%da/b' % i, (NH,))
+                a['o_wxh'] = put('cu/lstm_%da/wx' % i, (NH, 4 * NH))
+                o2 = put('cu/lstm_%da/wh' % i, (NH, 4 * NH)); assert o2 == a['o_wxh'] + NH * 4 * NH
+                a['o_b'] = put('cu/lstm_%da/b' % i, (4 * NH,)); assert a['o_b'] == o2 + NH * 4 * NH
+                hp, hv = 'cu/pi_%d' % i, 'cu/v_%da' % i
+            elif v == 'ia2c_fp':
+                s = 'lstm_%d' % i
+                a['o_w_msg'] = skip(NH * nm * NH); a['o_b_msg'] = skip(NH)
+                a['o_w_ob'] = put(s + '/fcs/w', (kx, NH)); a['o_b_ob'] = put(s + '/fcs/b', (NH,))
+                a['o_w_fp'] = put(s + '/fcp/w', (n_a * nm, NH)); a['o_b_fp'] = put(s + '/fcp/b', (NH,))
+                a['o_wxh'] = put(s + '/lstm/wx', (2 * NH, 4 * NH))
+                o1 = skip(NH * 4 * NH); assert o1 == a['o_wxh'] + 2 * NH * 4 * NH
+                o2 = put(s + '/lstm/wh', (NH, 4 * NH)); assert o2 == a['o_wxh'] + self.s_dim * 4 * NH
+                a['o_b'] = put(s + '/lstm/b', (4 * NH,))
+                hp, hv = s + '/pi', s + '/v'
+                a['t_w_msg'] = toff; toff += _up4(NH * NH * nm)
             else:
                 s = '%s/%s_%d' % (SCOPE[v], CELL[v], i)
                 km = NH if v == 'ma2c_ic3' else NH * nm
@@ -133,9 +175,9 @@ class ModelLayout:
                 poff += ((K + 31) // 32) * 2 * N * 32
                 return o
             a['tp_x'] = tp(kx, NH)
-            if v == 'ma2c_nc':
+            if self.vid == L.NC:
                 a['tp_p'] = tp(n_a * nm, NH)
-            if v != 'ia2c':
+            if self.vid != L.IA2C:
                 km2 = NH if v == 'ma2c_ic3' else NH * nm
                 a['tp_m'] = tp(km2, NH)
                 a['tp_mT'] = tp(NH, km2)
@@ -148,8 +190,8 @@ class ModelLayout:
         self.n_param, self.n_wt, self.n_wp = off, max(toff, 4), max(poff, 4)
         self.kx_pad = _up4(max(self._kx(i) for i in range(N)))
         max_nbr = max(len(x) for x in self.nbr)
-        self.kp_pad = _up4(n_a * max_nbr) if v == 'ma2c_nc' else 0
-        self.km_pad = {'ia2c': 0, 'ma2c_ic3': NH}.get(v, NH * max_nbr)
+        self.kp_pad = _up4(n_a * max_nbr) if self.vid == L.NC else 0
+        self.km_pad = {'ia2c': 0, 'ma2c_cu': 0, 'ma2c_ic3': NH}.get(v, NH * max_nbr)
         self.ld_in = self.kx_pad + self.kp_pad + self.km_pad
         if v == 'ia2c' and self.obs_mode == 'concat':
             self.obs_stride = _up4(max(self.n_s_ls))
@@ -162,7 +204,7 @@ class ModelLayout:
         m.variant, m.n_agent, m.n_a, m.s_dim = self.vid, self.N, self.n_a, self.s_dim
         m.obs_stride, m.kx_pad, m.kp_pad, m.km_pad = self.obs_stride, self.kx_pad, self.kp_pad, self.km_pad
         m.n_param, m.n_wt, m.n_wp = self.n_param, self.n_wt, self.n_wp
-        m.per_agent_norm = 1 if self.variant == 'ia2c' else 0
+        m.per_agent_norm = 1 if self.variant in PER_AGENT_OPT else 0
         recv = [[] for _ in range(self.N)]
         for k in range(self.N):
             for slot, j in enumerate(self.nbr[k]):
@@ -181,7 +223,7 @@ class ModelLayout:
                 ag.x_nsrc, ag.x_w = 1, self.n_s_ls[i]
                 ag.x_src[0] = i
             else:
-                srcs = [i] + self.nbr[i]
+                srcs = [i] if self.variant == 'ma2c_cu' else [i] + self.nbr[i]
                 ag.x_nsrc, ag.x_w = len(srcs), self.base_n_s
                 for s, j in enumerate(srcs):
                     ag.x_src[s] = j
@@ -208,6 +250,15 @@ class ModelLayout:
                 s = 'lstm_%d' % i
                 order += [s + '/fc/w', s + '/fc/b', s + '/lstm/wx', s + '/lstm/wh', s + '/lstm/b',
                           s + '/pi/w', s + '/pi/b', s + '/v/w', s + '/v/b']
+        elif v == 'ia2c_fp':            # fcs, fcp, lstm, heads per policy (agents/policies.py:173-185)
+            for i in range(N):
+                s = 'lstm_%d' % i
+                order += [s + '/fcs/w', s + '/fcs/b', s + '/fcp/w', s + '/fcp/b', s + '/lstm/wx', s + '/lstm/wh',
+                          s + '/lstm/b', s + '/pi/w', s + '/pi/b', s + '/v/w', s + '/v/b']
+        elif v == 'ma2c_cu':            # agent by agent inside one graph (agents/policies.py:378-396)
+            for i in range(N):
+                order += ['cu/fc_%da/w' % i, 'cu/fc_%da/b' % i, 'cu/lstm_%da/wx' % i, 'cu/lstm_%da/wh' % i,
+                          'cu/lstm_%da/b' % i, 'cu/pi_%d/w' % i, 'cu/pi_%d/b' % i, 'cu/v_%da/w' % i, 'cu/v_%da/b' % i]
         else:
             for i in range(N):
                 s = '%s/%s_%d' % (SCOPE[v], CELL[v], i)

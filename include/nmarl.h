@@ -229,6 +229,13 @@ int nmarl_clip_rmsprop_step(const nmarl_model* m, float* params, float* grads, f
                             const float* lr, float max_grad_norm, float rho, float eps,
                             float* norm_out, float* scratch, void* stream);
 
+/* ---- consensus update (IA2C_CU / `ma2c_cu`) ----------------------------------------------------
+ * Replaces ConsensusPolicy._consensus_update (agents/policies.py:351-359, 401-426), run after every
+ * optimizer step: agent i's LSTM variables (wx, wh, b -- one contiguous block of the flat buffer) become
+ * the mean of the blocks of {i} + its neighbours (ascending index), all read BEFORE any is written.
+ *   scratch: device float [n_agent * ((s_dim + 64) * 256 + 256)]                                         */
+int nmarl_consensus_update(const nmarl_model* m, float* params, float* scratch, void* stream);
+
 #pragma GCC visibility pop
 #ifdef __cplusplus
 }

@@ -12,12 +12,12 @@ import argparse
 import configparser
 import logging
 
-from deeprl_network_b200.agents.models import IA2C, MA2C_NC, MA2C_IC3, MA2C_DIAL
+from deeprl_network_b200.agents.models import IA2C, IA2C_FP, IA2C_CU, MA2C_NC, MA2C_IC3, MA2C_DIAL
 from deeprl_network_b200.envs.cacc_env import CACCEnv
 from deeprl_network_b200.utils import (Counter, Trainer, Evaluator, VecTrainer, check_dir, copy_file, find_file,
                                        init_dir, init_log, make_summary_writer)
 
-AGENTS = {'ia2c': IA2C, 'ma2c_nc': MA2C_NC, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}
+AGENTS = {'ia2c': IA2C, 'ia2c_fp': IA2C_FP, 'ma2c_cu': IA2C_CU, 'ma2c_nc': MA2C_NC, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}
 
 
 def parse_args():
@@ -52,7 +52,7 @@ def init_agent(env, config, total_step, seed, **kw):
     if cls is None:
         logging.error('agent %r is not on the accelerated hot path' % env.agent)
         return None
-    if env.agent == 'ia2c' and env.n_env > 1:
+    if env.agent == 'ia2c' and env.n_env > 1:     # device-resident rollouts gather neighbour observations in the kernel
         kw.setdefault('obs_mode', 'gather')
     return cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma,
                total_step, config, seed=seed, n_env=env.n_env, **kw)

@@ -155,7 +155,10 @@ class OracleCACC:
             return base
         out = []
         for i in range(self.n_agent):
-            parts = [base[i]] + [base[j] for j in np.where(self.neighbor_mask[i] == 1)[0]]
+            nb = np.where(self.neighbor_mask[i] == 1)[0]
+            parts = [base[i]] + [base[j] for j in nb]
+            if self.agent == 'ia2c_fp':          # fingerprints go at the end (envs/cacc_env.py:74-77)
+                parts += [self.fp[j] for j in nb]
             out.append(np.concatenate(parts))
         return out
 

@@ -23,7 +23,7 @@ Gate order is i,f,o,u; state layout is [c | h].
 import numpy as np
 import torch
 
-VARIANTS = ('ia2c', 'ma2c_nc', 'ma2c_ic3', 'ma2c_dial')
+VARIANTS = ('ia2c', 'ia2c_fp', 'ma2c_cu', 'ma2c_nc', 'ma2c_ic3', 'ma2c_dial')
 SCOPE = {'ma2c_nc': 'nc', 'ma2c_ic3': 'ic3', 'ma2c_dial': 'dial'}
 CELL = {'ma2c_nc': 'lstm_comm', 'ma2c_ic3': 'lstm_ic3', 'ma2c_dial': 'lstm_comm'}
 
@@ -49,6 +49,23 @@ def param_shapes(variant, n_s_ls, n_a, mask, n_h=64, n_fc=64):
                     (s + '/lstm/wx', (n_fc, 4 * n_h)), (s + '/lstm/wh', (n_h, 4 * n_h)), (s + '/lstm/b', (4 * n_h,)),
                     (s + '/pi/w', (n_h, n_a)), (s + '/pi/b', (n_a,)),
                     (s + '/v/w', (n_h + n_a * nm[i], 1)), (s + '/v/b', (1,))]
+        return out
+    if variant == 'ia2c_fp':     # FPPolicy (agents/policies.py:157-185); n_s_ls already counts the fingerprints
+        for i in range(N):
+            s = 'lstm_%d' % i
+            n_x = n_s_ls[i] - n_a * nm[i]
+            out += [(s + '/fcs/w', (n_x, n_fc)), (s + '/fcs/b', (n_fc,)),
+                    (s + '/fcp/w', (n_a * nm[i], n_fc)), (s + '/fcp/b', (n_fc,)),
+                    (s + '/lstm/wx', (2 * n_fc, 4 * n_h)), (s + '/lstm/wh', (n_h, 4 * n_h)), (s + '/lstm/b', (4 * n_h,)),
+                    (s + '/pi/w', (n_h, n_a)), (s + '/pi/b', (n_a,)),
+                    (s + '/v/w', (n_h + n_a * nm[i], 1)), (s + '/v/b', (1,))]
+        return out
+    if variant == 'ma2c_cu':     # ConsensusPolicy._build_net (agents/policies.py:366-399)
+        for i in range(N):
+            out += [('cu/fc_%da/w' % i, (n_s_ls[i], n_h)), ('cu/fc_%da/b' % i, (n_h,)),
+                    ('cu/lstm_%da/wx' % i, (n_h, 4 * n_h)), ('cu/lstm_%da/wh' % i, (n_h, 4 * n_h)), ('cu/lstm_%da/b' % i, (4 * n_h,)),
+                    ('cu/pi_%d/w' % i, (n_h, n_a)), ('cu/pi_%d/b' % i, (n_a,)),
+                    ('cu/v_%da/w' % i, (n_h + n_a * nm[i], 1)), ('cu/v_%da/b' % i, (1,))]
         return out
     sc, cell = SCOPE[variant], CELL[variant]
     n_s = n_s_ls[0]
@@ -111,13 +128,19 @@ class OraclePolicy:
         self.states_fw, self.states_bw = z.clone(), z.clone()
 
     def _w(self, i, key):
-        if self.variant == 'ia2c':
+        if self.variant in ('ia2c', 'ia2c_fp'):
             return self.p['lstm_%d/%s' % (i, key)]
+        if self.variant == 'ma2c_cu':
+            a, b = key.split('/')
+            return self.p['cu/%s_%da/%s' % (a, i, b)]
         return self.p['%s/%s_%d/%s' % (SCOPE[self.variant], CELL[self.variant], i, key)]
 
     def _head(self, i, key):
-        if self.variant == 'ia2c':
+        if self.variant in ('ia2c', 'ia2c_fp'):
             return self.p['lstm_%d/%s' % (i, key)]
+        if self.variant == 'ma2c_cu':
+            a, b = key.split('/')
+            return self.p['cu/%s_%d%s/%s' % (a, i, 'a' if a == 'v' else '', b)]
         sc = SCOPE[self.variant]
         a, b = key.split('/')
         return self.p['%s/%s_%d/%s' % (sc, a, i, b)]
@@ -135,8 +158,14 @@ class OraclePolicy:
         for i in range(self.N):
             ci, hi = c[:, i] * nd, h[:, i] * nd
             nb = self.nbr[i]
-            if v == 'ia2c':
+            if v in ('ia2c', 'ma2c_cu'):
                 s = torch.relu(x[i] @ self._w(i, 'fc/w') + self._w(i, 'fc/b'))
+                wx, wh, b = self._w(i, 'lstm/wx'), self._w(i, 'lstm/wh'), self._w(i, 'lstm/b')
+            elif v == 'ia2c_fp':
+                n_x = x[i].shape[1] - self.n_a * len(nb)
+                hx = torch.relu(x[i][:, :n_x] @ self._w(i, 'fcs/w') + self._w(i, 'fcs/b'))
+                hp = torch.relu(x[i][:, n_x:] @ self._w(i, 'fcp/w') + self._w(i, 'fcp/b'))
+                s = torch.cat([hx, hp], dim=1)
                 wx, wh, b = self._w(i, 'lstm/wx'), self._w(i, 'lstm/wh'), self._w(i, 'lstm/b')
             else:
                 xi = torch.cat([x[i]] + [x[j] for j in nb], dim=1)
@@ -221,8 +250,24 @@ class OraclePolicy:
         v_loss = ((R - v) ** 2).mean(dim=(0, 1)) * 0.5 * v_coef
         return p_loss, v_loss, e_loss
 
+    def consensus_update(self):
+        """ConsensusPolicy._consensus_update (agents/policies.py:351-359, 401-426): every LSTM variable of
+        agent i := mean over [i] + neighbours (ascending) of that variable.  The reference groups the assigns
+        in one session.run without ordering them; the intended simultaneous update is restated here (all
+        means are taken from the pre-update values)."""
+        new = {}
+        for i in range(self.N):
+            agents = [i] + list(self.nbr[i])
+            for key in ('wx', 'wh', 'b'):
+                acc = self.p['cu/lstm_%da/%s' % (agents[0], key)].detach().clone()
+                for j in agents[1:]:
+                    acc = acc + self.p['cu/lstm_%da/%s' % (j, key)].detach()
+                new['cu/lstm_%da/%s' % (i, key)] = acc / float(len(agents))
+        for n, val in new.items():
+            self.p[n].copy_(val)
+
     def _groups(self):
-        if self.variant == 'ia2c':      # one loss/clip/optimizer per agent (models.py:34-42)
+        if self.variant in ('ia2c', 'ia2c_fp'):      # one loss/clip/optimizer per agent (models.py:34-42)
             return [[n for n in self.names if n.startswith('lstm_%d/' % i)] for i in range(self.N)]
         return [self.names]
 
@@ -248,6 +293,8 @@ class OraclePolicy:
                         g = self.grads[n] * scale
                         self.ms[n].mul_(alpha).add_((1 - alpha) * g * g)
                         self.p[n].sub_(lr * g / torch.sqrt(self.ms[n] + epsilon))
+            if apply and self.variant == 'ma2c_cu':
+                self.consensus_update()
         self.states_bw = self.states_fw.clone()
         self.last_pi, self.last_v = pi.detach(), v.detach()
         return dict(policy_loss=p_loss.detach().numpy(), value_loss=v_loss.detach().numpy(),

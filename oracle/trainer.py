@@ -33,6 +33,8 @@ class OracleAgent:
         self.n_agent = len(neighbor_mask)
         self.n_step = int(model_config['batch_size'])
         self.reward_norm, self.reward_clip = g('reward_norm'), g('reward_clip')
+        if variant == 'ia2c_fp':      # agents/models.py:172-177
+            n_s_ls = [n + n_a_ls[0] * int(np.sum(np.asarray(neighbor_mask)[i])) for i, n in enumerate(n_s_ls)]
         self.policy = OraclePolicy(variant, n_s_ls, n_a_ls[0], neighbor_mask,
                                    n_h=int(model_config['num_lstm']), n_fc=int(model_config['num_fc']),
                                    params=params, dtype=dtype)
@@ -48,7 +50,7 @@ class OracleAgent:
         self.last_summary = None
 
     def forward(self, obs, done, ps_or_nactions=None, actions=None, out_type='p'):
-        if self.name == 'ia2c':
+        if self.name.startswith('ia2c'):
             # IA2C signature: forward(obs, done, nactions=None, out_type='p') (models.py:44-51)
             if isinstance(actions, str):
                 out_type, actions = actions, None
@@ -70,7 +72,7 @@ class OracleAgent:
             reward = reward / self.reward_norm
         if self.reward_clip > 0:
             reward = np.clip(reward, -self.reward_clip, self.reward_clip)
-        if self.name == 'ia2c':
+        if self.name.startswith('ia2c'):
             p = np.zeros((self.n_agent, self.policy.n_a))    # unused placeholder
         self.trans_buffer.add_transition([np.asarray(o) for o in ob], np.array(p), np.asarray(action),
                                          reward, np.asarray(value), done)
@@ -86,7 +88,7 @@ class OracleAgent:
         Advs_t = np.transpose(Advs)[:, None]
         dones_t = dones.astype(np.float64)[:, None]
         self.last_batch = dict(Rs=Rs, Advs=Advs, dones=dones)
-        self.last_summary = self.policy.backward(obs_t, None if self.name == 'ia2c' else ps_t, acts_t, dones_t,
+        self.last_summary = self.policy.backward(obs_t, None if self.name.startswith('ia2c') else ps_t, acts_t, dones_t,
                                                  Rs_t, Advs_t, lr, apply=apply, **self.hp)
         self.last_summary['lr'] = lr
         return self.last_summary

@@ -7,7 +7,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 CFG = {'ma2c_nc': 'config_ma2c_nc_catchup.ini', 'ia2c': 'config_ia2c_catchup.ini',
-       'ma2c_ic3': 'config_ma2c_cnet_slowdown.ini', 'ma2c_dial': 'config_ma2c_dial_catchup.ini'}
+       'ma2c_ic3': 'config_ma2c_cnet_slowdown.ini', 'ma2c_dial': 'config_ma2c_dial_catchup.ini',
+       'ia2c_fp': 'config_ia2c_fp_slowdown.ini', 'ma2c_cu': 'config_ia2c_cu_catchup.ini'}
 
 
 def load_cfg(name, **env_over):

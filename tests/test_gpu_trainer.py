@@ -41,12 +41,14 @@ class Rec:
 
 
 @pytest.mark.parametrize('agent,cfg', [('ma2c_nc', None), ('ia2c', None), ('ma2c_ic3', None), ('ma2c_dial', None),
-                                       ('ia2c', 'config_ia2c_slowdown.ini')])       # last: spatial returns, per-agent rewards
+                                       ('ia2c', 'config_ia2c_slowdown.ini'),        # spatial returns, per-agent rewards
+                                       ('ia2c_fp', None), ('ma2c_cu', None)])
 def test_trainer_lockstep_with_oracle(agent, cfg):
-    from deeprl_network_b200.agents.models import IA2C, MA2C_DIAL, MA2C_IC3, MA2C_NC
+    from deeprl_network_b200.agents.models import IA2C, IA2C_CU, IA2C_FP, MA2C_DIAL, MA2C_IC3, MA2C_NC
     from deeprl_network_b200.envs.cacc_env import CACCEnv
     from deeprl_network_b200.utils import Counter, Trainer
-    cls = {'ma2c_nc': MA2C_NC, 'ia2c': IA2C, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}[agent]
+    cls = {'ma2c_nc': MA2C_NC, 'ia2c': IA2C, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL, 'ia2c_fp': IA2C_FP,
+           'ma2c_cu': IA2C_CU}[agent]
     cp = load_cfg(cfg or CFG[agent])
     # CUDA side (weights drawn from np.random right after the env seeds it -- reference order)
     env = CACCEnv(cp['ENV_CONFIG'])
@@ -75,6 +77,13 @@ def test_trainer_lockstep_with_oracle(agent, cfg):
     for k, v in oag.policy.p.items():
         np.testing.assert_allclose(w[k], v.detach().numpy(), rtol=0, atol=2e-5, err_msg=k)
     assert env.seed == oenv.seed == 12 + 4                      # quirk Q3: two resets per training episode
+    if agent == 'ia2c_fp':        # the null message encoder behind FPPolicy must not have moved (layout.py docstring)
+        flat = model.engine.params.cpu().numpy()
+        named = np.zeros(flat.size, dtype=bool)
+        for _, o, shape in model.layout.entries:
+            named[o:o + int(np.prod(shape))] = True
+        assert not flat[~named].any()
+        assert model.engine.grads.cpu().numpy()[~named].any() == False
 
 
 def test_save_load_roundtrip(tmp_path):

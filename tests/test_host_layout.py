@@ -13,12 +13,14 @@ from deeprl_network_b200.envs.cacc_env import chain_masks, grid_masks
 from deeprl_network_b200.layout import ModelLayout
 from oracle import nets
 
-N_PARAM = {'ma2c_nc': 598496, 'ma2c_ic3': 307680, 'ma2c_dial': 365536, 'ia2c': 274400}
+N_PARAM = {'ma2c_nc': 598496, 'ma2c_ic3': 307680, 'ma2c_dial': 365536, 'ia2c': 274400,
+           'ia2c_fp': 409568, 'ma2c_cu': 269920}     # 2 edge + 6 inner agents, counted by hand from policies.py:157-185, 366-399
+N_S_LS = {'ia2c': [10, 15, 15, 15, 15, 15, 15, 10], 'ia2c_fp': [14, 23, 23, 23, 23, 23, 23, 14]}
 
 
 def _layout(variant, **kw):
     mask, _ = chain_masks(8)
-    n_s_ls = [5] * 8 if variant != 'ia2c' else [10, 15, 15, 15, 15, 15, 15, 10]
+    n_s_ls = N_S_LS.get(variant, [5] * 8)
     return ModelLayout(variant, n_s_ls, 4, mask, **kw), mask, n_s_ls
 
 
@@ -46,7 +48,7 @@ def test_pack_unpack_roundtrip_and_init_order(variant):
     for k in ref:
         np.testing.assert_array_equal(mine[k], ref[k])
     np.testing.assert_array_equal(lay.pack(mine), flat)
-    w = mine[[k for k in mine if k.endswith('wx_hid') or k.endswith('lstm/wx')][0]]
+    w = mine[[k for k in mine if k.endswith('wx_hid') or k.endswith('/wx')][0]]
     np.testing.assert_allclose(w.T @ w if w.shape[0] >= w.shape[1] else w @ w.T, 2 * np.eye(min(w.shape)), atol=1e-4)
 
 
@@ -74,10 +76,29 @@ def test_ia2c_gather_and_concat_layouts_share_weights():
     assert b.c_model().agent[1].x_nsrc == 3 and b.c_model().agent[1].x_w == 5 and b.obs_stride == 8
 
 
+def test_fp_and_consensus_agents_reuse_kernel_families():
+    """ia2c_fp is laid out as a NeurComm cell with unnamed zero padding where the message encoder
+    and wx rows 128..191 sit; ma2c_cu is the IA2C cell fed with the agent's own observation."""
+    lay, _, _ = _layout('ia2c_fp')
+    m = lay.c_model()
+    assert (m.variant, m.s_dim, m.per_agent_norm, m.kx_pad, m.kp_pad, m.km_pad) == (L.NC, 192, 1, 16, 8, 128)
+    flat = lay.pack({n: np.ones(s, dtype=np.float32) for n, _, s in lay.entries})
+    a = lay.agents_off[3]
+    assert not flat[a['o_w_msg']:a['o_w_msg'] + 128 * 64].any() and not flat[a['o_b_msg']:a['o_b_msg'] + 64].any()
+    assert flat[a['o_wxh']:a['o_wxh'] + 128 * 256].all() and not flat[a['o_wxh'] + 128 * 256:a['o_wxh'] + 192 * 256].any()
+    assert flat[a['o_wxh'] + 192 * 256:a['o_wxh'] + 256 * 256].all()          # wh directly behind the padded wx
+    assert int(flat.sum()) == lay.n_real_param() < lay.n_param
+    lay, _, _ = _layout('ma2c_cu')
+    m = lay.c_model()
+    assert (m.variant, m.s_dim, m.per_agent_norm, m.kx_pad) == (L.IA2C, 64, 0, 8)
+    assert m.agent[3].x_nsrc == 1 and m.agent[3].x_w == 5 and m.agent[3].n_nbr == 2
+    assert m.agent[3].o_b == m.agent[3].o_wxh + 128 * 256                        # block nmarl_consensus_update averages
+
+
 def test_unsupported_configurations_fail_loudly():
     mask, _ = chain_masks(8)
     with pytest.raises(ValueError):
-        ModelLayout('ia2c_fp', [5] * 8, 4, mask)
+        ModelLayout('greedy', [5] * 8, 4, mask)
     with pytest.raises(ValueError):
         ModelLayout('ma2c_nc', [5] * 8, 4, mask, n_h=128)
 
