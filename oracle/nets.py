@@ -162,9 +162,12 @@ class OraclePolicy:
                 s = torch.relu(x[i] @ self._w(i, 'fc/w') + self._w(i, 'fc/b'))
                 wx, wh, b = self._w(i, 'lstm/wx'), self._w(i, 'lstm/wh'), self._w(i, 'lstm/b')
             elif v == 'ia2c_fp':
-                n_x = x[i].shape[1] - self.n_a * len(nb)
+                n_x = self.n_s_ls[i] - self.n_a * len(nb)
+                # the environment attaches the fingerprints to the observation; tests that keep them in a
+                # separate array pass observations of width n_x plus ps
+                fp_in = x[i][:, n_x:] if x[i].shape[1] > n_x else torch.cat([p[:, j] for j in nb], dim=1)
                 hx = torch.relu(x[i][:, :n_x] @ self._w(i, 'fcs/w') + self._w(i, 'fcs/b'))
-                hp = torch.relu(x[i][:, n_x:] @ self._w(i, 'fcp/w') + self._w(i, 'fcp/b'))
+                hp = torch.relu(fp_in @ self._w(i, 'fcp/w') + self._w(i, 'fcp/b'))
                 s = torch.cat([hx, hp], dim=1)
                 wx, wh, b = self._w(i, 'lstm/wx'), self._w(i, 'lstm/wh'), self._w(i, 'lstm/b')
             else:

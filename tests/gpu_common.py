@@ -18,7 +18,8 @@ def make_pair(variant, B, T=4, seed=0, dtype=torch.float32, mask=None, n_a=4, hp
     if mask is None:
         mask, _ = chain_masks(8)
     N = len(mask)
-    n_s_ls = [5 * (1 + int(mask[i].sum())) for i in range(N)] if variant == 'ia2c' else [5] * N
+    nm = [int(mask[i].sum()) for i in range(N)]
+    n_s_ls = {'ia2c': [5 * (1 + k) for k in nm], 'ia2c_fp': [5 * (1 + k) + n_a * k for k in nm]}.get(variant, [5] * N)
     lay = ModelLayout(variant, n_s_ls, n_a, mask, obs_mode='gather')
     params = random_params(lay.creation_order(), seed=seed, scale=scale)
     eng = PolicyEngine(lay, B, T, dict(HP if hp is None else hp), flat_params=lay.pack(params))
@@ -28,7 +29,7 @@ def make_pair(variant, B, T=4, seed=0, dtype=torch.float32, mask=None, n_a=4, hp
 
 def oracle_obs(lay, base):
     """base [B, N, 5] own features -> per-agent oracle inputs (IA2C: own + neighbours concatenated)."""
-    if lay.variant != 'ia2c':
+    if lay.variant not in ('ia2c', 'ia2c_fp'):      # ia2c_fp: the fingerprints travel separately (ps)
         return [base[:, i] for i in range(lay.N)]
     return [np.concatenate([base[:, i]] + [base[:, j] for j in lay.nbr[i]], axis=1) for i in range(lay.N)]
 

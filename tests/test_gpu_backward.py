@@ -7,7 +7,7 @@ import torch
 from gpu_common import HP, bn, make_pair, nb, oracle_obs, to_dev
 
 pytestmark = pytest.mark.gpu
-VARIANTS = ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c']
+VARIANTS = ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c', 'ia2c_fp', 'ma2c_cu']
 
 
 def _batch(eng, lay, T, B, seed=0, N=8):

@@ -9,7 +9,7 @@ from gpu_common import bn, make_pair, nb, obs_dev, oracle_obs, to_dev
 from oracle.trainer import OracleTrainer
 
 pytestmark = pytest.mark.gpu
-VARIANTS = ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c']
+VARIANTS = ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c', 'ia2c_fp', 'ma2c_cu']
 TOL = 1e-5
 
 

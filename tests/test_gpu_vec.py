@@ -16,10 +16,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _make(agent, B, graph=False, sample='philox', **over):
-    from deeprl_network_b200.agents.models import IA2C, MA2C_DIAL, MA2C_IC3, MA2C_NC
+    from deeprl_network_b200.agents.models import IA2C, IA2C_CU, IA2C_FP, MA2C_DIAL, MA2C_IC3, MA2C_NC
     from deeprl_network_b200.envs.cacc_env import CACCEnv
     from deeprl_network_b200.utils import VecTrainer
-    cls = {'ma2c_nc': MA2C_NC, 'ia2c': IA2C, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}[agent]
+    cls = {'ma2c_nc': MA2C_NC, 'ia2c': IA2C, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL, 'ia2c_fp': IA2C_FP,
+           'ma2c_cu': IA2C_CU}[agent]
     cp = load_cfg(CFG[agent], n_env=B, **over)
     env = CACCEnv(cp['ENV_CONFIG'])
     kw = dict(obs_mode='gather') if agent == 'ia2c' else {}
@@ -28,7 +29,14 @@ def _make(agent, B, graph=False, sample='philox', **over):
     return cp, env, model, VecTrainer(env, model, graph=graph, sample=sample)
 
 
-@pytest.mark.parametrize('agent', ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c'])
+def _n_s(agent, oenv):
+    """IA2C_FP counts the attached fingerprints in the state width (agents/models.py:172-177)."""
+    if agent != 'ia2c_fp':
+        return oenv.n_s_ls
+    return [n + 4 * int(np.sum(oenv.neighbor_mask[i])) for i, n in enumerate(oenv.n_s_ls)]
+
+
+@pytest.mark.parametrize('agent', ['ma2c_nc', 'ma2c_ic3', 'ma2c_dial', 'ia2c', 'ia2c_fp', 'ma2c_cu'])
 def test_batched_rollout_and_update_vs_oracle(agent):
     B = 5
     cp, env, model, vt = _make(agent, B, sample='uniform')
@@ -50,7 +58,7 @@ def test_batched_rollout_and_update_vs_oracle(agent):
     obs_rec = [[None] * B for _ in range(T)]
     for b in range(B):
         oenv = OracleCACC(cp['ENV_CONFIG']); ob = oenv.reset(u01=u0[0, b])
-        pol = nets.OraclePolicy(agent, oenv.n_s_ls, 4, mask, params=w0)
+        pol = nets.OraclePolicy(agent, _n_s(agent, oenv), 4, mask, params=w0)
         done, fp = True, np.ones((N, 4)) / 4
         rews, vs, dones = [], [], []
         for t in range(T):
@@ -61,6 +69,7 @@ def test_batched_rollout_and_update_vs_oracle(agent):
             v = pol.forward(ob, done, fp[None], a[None], 'v')[0]
             np.testing.assert_allclose(vals[t, :, b], v, rtol=0, atol=1e-5)
             fp = pi
+            oenv.update_fingerprint(pi)
             ob, r, done, gr = oenv.step(a)
             assert abs(grew[t, b] - gr) <= 1e-9 * abs(gr)
             rews.append(np.broadcast_to(np.asarray(r) / g('reward_norm'), (N,))); vs.append(v); dones.append(done)
@@ -73,7 +82,7 @@ def test_batched_rollout_and_update_vs_oracle(agent):
         np.testing.assert_allclose(Rs[:, :, b].T, oR, rtol=0, atol=1e-5)
         np.testing.assert_allclose(Advs[:, :, b].T, oA, rtol=0, atol=2e-5)
     # batched gradient on the recorded trajectories (oracle consumes the kernel's own Rs / Advs)
-    pol = nets.OraclePolicy(agent, OracleCACC(cp['ENV_CONFIG']).n_s_ls, 4, mask, params=w0, n_env=B, dtype=torch.float64)
+    pol = nets.OraclePolicy(agent, _n_s(agent, OracleCACC(cp['ENV_CONFIG'])), 4, mask, params=w0, n_env=B, dtype=torch.float64)
     obs_t = [[np.stack([obs_rec[t][b][i] for b in range(B)]) for i in range(N)] for t in range(T)]
     fp_t = np.transpose(e.fp_buf[:T].cpu().numpy(), (0, 2, 1, 3))
     dones_t = e.done_buf[:T].cpu().numpy()
