@@ -15,7 +15,7 @@
 namespace {
 using namespace tcrow;
 
-enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_P, J_ENC_M0, J_ENC_M1, J_COUNT };
+enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_M0, J_ENC_M1, J_COUNT };
 
 struct TcWgK {
   int B, T, splits, ndp;
@@ -28,12 +28,14 @@ struct TcWgK {
 
 struct JobDesc {
   const float* A; int F_A, a_feat0, ka_cnt, ones;
+  int p_feat0, p_cnt;             // obs-encoder job only: fingerprint features ride on the lanes behind the ones lane
   const float* BT; int tile_rows, n_row0, N;
 };
 
 __device__ __forceinline__ JobDesc job_desc(const nmarl_model& m, const TcWgK& k, int kind, int i) {
   const nmarl_agent& ag = m.agent[i];
   JobDesc d;
+  d.p_feat0 = 0; d.p_cnt = 0;
   const int SD = m.s_dim, LDI = m.kx_pad + m.kp_pad + m.km_pad;
   const int Km = (m.variant == NMARL_IC3) ? NH : ag.n_nbr * NH;
   if (kind == J_GATE0 || kind == J_GATE1) {
@@ -42,10 +44,8 @@ __device__ __forceinline__ JobDesc job_desc(const nmarl_model& m, const TcWgK& k
     d.BT = k.dzT; d.tile_rows = 256; d.n_row0 = 0; d.N = 256;
   } else if (kind == J_ENC_X) {
     d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = 0; d.ka_cnt = ag.x_nsrc * ag.x_w; d.ones = 1;
+    if (m.variant == NMARL_NC) { d.p_feat0 = m.kx_pad; d.p_cnt = ag.n_nbr * m.n_a; }
     d.BT = k.dpT; d.tile_rows = k.ndp; d.n_row0 = 0; d.N = k.ndp;
-  } else if (kind == J_ENC_P) {
-    d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = m.kx_pad; d.ka_cnt = ag.n_nbr * m.n_a; d.ones = 0;
-    d.BT = k.dpT; d.tile_rows = k.ndp; d.n_row0 = 64; d.N = 64;
   } else {
     const int mt = kind - J_ENC_M0;
     d.A = k.sv_xin; d.F_A = LDI; d.a_feat0 = m.kx_pad + m.kp_pad + 128 * mt; d.ka_cnt = max(0, min(128, Km - 128 * mt)); d.ones = 0;
@@ -96,12 +96,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     const int ka = quarter * 32 + lane;                               // TMEM lane == feature within this M tile
     c.tmem = tmem; c.lane_base = (uint32_t)(quarter * 32) << 16;
     c.a_full = a_full; c.a_empty = a_empty; c.enc_full = enc_full; c.q = 0; c.e = 0; c.set = set; c.err = k.err;
-    const bool real = ka < d.ka_cnt, one = d.ones && ka == d.ka_cnt;
+    const bool one = d.ones && ka == d.ka_cnt;
+    const bool is_p = ka > d.ka_cnt && ka <= d.ka_cnt + d.p_cnt;
+    const bool real = ka < d.ka_cnt || is_p;
+    const int feat = is_p ? d.p_feat0 + (ka - d.ka_cnt - 1) : d.a_feat0 + ka;
     for (int q = 0; q < nkb; ++q) {
       const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
       float x[W];
       if (real) {
-        const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + d.a_feat0 + ka) * k.B + rb * 32 + set * W;
+        const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * W;
 #pragma unroll
         for (int p = 0; p < W / 4; ++p) {
           const float4 v = *reinterpret_cast<const float4*>(src + 4 * p);
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       produce_in(c, x);
     }
     // tcgen05.ld is warp-collective (.sync.aligned): the condition must be warp-uniform; stores are per lane
-    const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0);
+    const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;
     if (warp_active) {
       float* out = wsj + (size_t)ka * d.N;
       if (nkb > 0) {
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
   const int jslot = blockIdx.y, i = blockIdx.z, kind = k.jobs[jslot];
   const JobDesc d = job_desc(m, k, kind, i);
   const nmarl_agent& ag = m.agent[i];
-  const int lanes = d.ka_cnt + (d.ones ? 1 : 0);
+  const int lanes = d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;
   const int total = lanes * d.N;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int ln = e / d.N, n = e - ln * d.N;
@@ -185,11 +188,11 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
     if (kind == J_GATE0 || kind == J_GATE1) grads[ag.o_wxh + (size_t)(128 * (kind - J_GATE0) + ln) * NG + n] = s;
     else if (kind == J_ENC_X) {
       if (ln < d.ka_cnt) { if (n < NH) grads[ag.o_w_ob + ln * NH + n] = s; }
+      else if (ln > d.ka_cnt) { if (n >= NH && n < 2 * NH) grads[ag.o_w_fp + (ln - d.ka_cnt - 1) * NH + n - NH] = s; }   // fingerprint lanes
       else if (n < NH) grads[ag.o_b_ob + n] = s;                                       // ones lane: biases
       else if (m.variant == NMARL_NC && n < 2 * NH) grads[ag.o_b_fp + n - NH] = s;
       else grads[ag.o_b_msg + n - ((m.variant == NMARL_NC) ? 2 * NH : NH)] = s;
-    } else if (kind == J_ENC_P) grads[ag.o_w_fp + ln * NH + n] = s;
-    else grads[ag.o_w_msg + (size_t)(128 * (kind - J_ENC_M0) + ln) * NH + n] = s;
+    } else grads[ag.o_w_msg + (size_t)(128 * (kind - J_ENC_M0) + ln) * NH + n] = s;
   }
 }
 
@@ -218,7 +221,7 @@ int job_list(const nmarl_model* m, int* jobs) {
   jobs[n++] = J_GATE0;
   if (m->s_dim + NH > 128) jobs[n++] = J_GATE1;
   jobs[n++] = J_ENC_X;
-  if (m->variant == NMARL_NC) jobs[n++] = J_ENC_P;
+  // (the fingerprint encoder shares the obs-encoder job: its few features sit on spare lanes of that tile)
   if (m->variant != NMARL_IA2C) {
     jobs[n++] = J_ENC_M0;
     if (m->km_pad > 128) jobs[n++] = J_ENC_M1;
@@ -250,7 +253,8 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
 }
 
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
-                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st) {
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st,
+                           cudaStream_t st_bias) {
   TcWgK k{};
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
@@ -262,13 +266,13 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
     NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
+  dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B, T, grads);   // independent of the GEMM jobs
+  NMARL_LAUNCH_CHECK();
   tc_wgrad_kernel<<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   NMARL_DBG_SYNC(st, "tc_wgrad_kernel");
   tc_wgrad_reduce_kernel<<<dim3(64, k.n_jobs, m->n_agent), 256, 0, st>>>(*m, k, grads);
   NMARL_LAUNCH_CHECK();
   NMARL_DBG_SYNC(st, "tc_wgrad_reduce");
-  dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st>>>(*m, sv_dz, B, T, grads);
-  NMARL_LAUNCH_CHECK();
   return 0;
 }
