@@ -159,7 +159,11 @@ def main():
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
-    os.environ['NCCL_DEBUG'] = os.environ.get('NMARL_NCCL_DEBUG', 'WARN')     # keep stdout to the one JSON line
+    # stdout carries exactly one JSON line: NCCL (version banner, NCCL_DEBUG output) and any library chatter write to
+    # file descriptor 1 as well, so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -281,7 +285,8 @@ def main():
                'label': 'restated reference (TF unavailable)', 'seconds': dt}
 
     if rank == 0:
-        print(json.dumps({
+        emit = lambda line: os.write(json_fd, (line + '\n').encode())
+        emit(json.dumps({
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
