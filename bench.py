@@ -245,17 +245,38 @@ def main():
                'ms_per_step': ms2 / args.steps,
                'api': 'VecTrainer.update(uniforms=<host RNG stream>) -> rewards, loss terms'}
 
-    # ---- roofline of the dominant kernel: fused gather + encoders + LSTM cell + heads (p-call) --------
-    n_rep = 50
+    # ---- roofline of the dominant kernel: fused gather + encoders + LSTM cell + heads (rollout p-call) ----
+    # Timed IN SITU: one more rollout, launched eagerly, with CUDA events on the launching stream around each of its
+    # T p-calls (every call works on its own state / activation slots, so the caches are in their real state); the
+    # v-calls stay on the main stream for this pass so nothing shares the SMs with the kernel being timed.
     pi = torch.zeros(N, B, e.n_a, device='cuda'); act = torch.zeros(N, B, dtype=torch.int32, device='cuda')
+    ms_warm = None
+    if getattr(e, 'fuse_save', False) and e.use_tc:
+        ov = e.overlap_v
+        e.overlap_v, e.kernel_events = False, []
+        e.rollout(env, sample=vt.sample)
+        torch.cuda.synchronize()
+        e.overlap_v = ov
+        durs = [a.elapsed_time(b) for a, b in e.kernel_events[:T]]          # the T saving p-calls (not the bootstrap)
+        e.kernel_events = None
+        e.saved_rollout = False
+        ms_k = float(np.mean(durs))
+        saves = True
+    else:
+        saves = False
 
     def pcall():
         e.step_p(e.obs_buf[0], e.fp_buf[0], e.done_buf[0], pi, act, L.SAMPLE_PHILOX, rng_offset=0)
     for _ in range(5):
         pcall()
-    ms_k = timed(pcall, n_rep) / n_rep
+    ms_warm = timed(pcall, 50) / 50                       # same kernel without the saves, back to back on one input
+    if not saves:
+        ms_k = ms_warm
     bytes_per_agent_step = 1640 if env.agent == 'ma2c_nc' else {'ma2c_ic3': 1612, 'ma2c_dial': 1628}.get(env.agent, 1100)
-    alg_bytes = bytes_per_agent_step * N * B              # K1+K2+state+outputs per agent-env-step
+    # K1+K2+state+outputs per agent-env-step; the rollout p-call also writes the activations BPTT needs
+    # (8(d) "Backward": s, gates, c, h, encoder pre-activations ~ 768 floats, booked there under the training forward)
+    save_bytes = 3072 if saves else 0
+    alg_bytes = (bytes_per_agent_step + save_bytes) * N * B
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -265,18 +286,23 @@ def main():
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(
-            'tc_cell_fwd_p_bytes_per_launch' if e.use_tc else 'cell_fwd_p_bytes_per_launch')
+            ('tc_cell_fwd_ps_bytes_per_launch' if saves else 'tc_cell_fwd_p_bytes_per_launch') if e.use_tc
+            else 'cell_fwd_p_bytes_per_launch')
     except Exception:
         pass
     achieved = alg_bytes / (ms_k * 1e-3) / 1e9
-    roofline = {'kernel': ('tc_cell_fwd_kernel<P> (tcgen05 3xTF32: fused gather+encoders+LSTM cell+heads+sampling)'
+    roofline = {'kernel': (('tc_cell_fwd_kernel<PS> (tcgen05 3xTF32: fused gather+encoders+LSTM cell+heads+sampling+activation save)'
+                            if saves else 'tc_cell_fwd_kernel<P> (tcgen05 3xTF32: fused gather+encoders+LSTM cell+heads+sampling)')
                            if e.use_tc else 'cell_fwd_kernel<P> (FP32 FFMA)'), 'bound': 'hbm',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                'us_per_launch': ms_k * 1e3, 'algorithmic_bytes_per_launch': alg_bytes,
+                'us_per_launch': ms_k * 1e3, 'us_per_launch_warm_no_saves': ms_warm * 1e3,
+                'timing': 'CUDA events around each p-call of one eagerly launched rollout (in situ)' if saves else 'back-to-back launches',
+                'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_bytes_per_agent_step': bytes_per_agent_step + save_bytes,
                 'peak_source': 'MEASURED_PEAKS.json (burst)' if peaks else 'fallback 6.65 TB/s',
                 'tensor_tflops_3xtf32': 3 * 2 * 74359 * N * B / (ms_k * 1e-3) / 1e12,
-                'note': 'algorithmic bytes per SURVEY 8(d) (1640 B per agent-env-step); the kernel issues 3 TF32 MMAs per '
-                        'fp32 product (148.7 kFLOP fp32-equivalent per agent-step), see DESIGN.md'}
+                'note': 'algorithmic bytes per SURVEY 8(d): %d B forward + %d B saved activations per agent-env-step; the kernel '
+                        'issues 3 TF32 MMAs per fp32 product (148.7 kFLOP fp32-equivalent per agent-step), see DESIGN.md'
+                        % (bytes_per_agent_step, save_bytes)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

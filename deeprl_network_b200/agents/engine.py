@@ -94,6 +94,7 @@ class PolicyEngine:
         # v-calls run on a second stream: v(t) only feeds val_buf, so it overlaps env.step(t) and p(t+1)
         self.overlap_v = os.environ.get('NMARL_NO_OVERLAP', '0') != '1'
         self._vstream = None
+        self.kernel_events = None          # bench.py: list collecting (start, end) CUDA events around each rollout p-call
         self.T_cur = T
         self.launches = 0
         self.repack()
@@ -234,7 +235,13 @@ class PolicyEngine:
             if kw.get('save', False):
                 a.sv_xin, a.sv_sh, a.sv_gates = L.ptr(self.sv_xin[t]), L.ptr(self.sv_sh[t]), L.ptr(self.sv_gates[t])
                 a.sv_enc = L.ptr(None if self.sv_enc is None else self.sv_enc[t])
+            if self.kernel_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             L.check(L.lib().nmarl_policy_step_p(C.byref(self.model), C.byref(a), L.stream()), 'nmarl_policy_step_p')
+            if self.kernel_events is not None:
+                ev[1].record()
+                self.kernel_events.append(ev)
         else:
             a.c_in, a.h_in, a.msg_in = L.ptr(self.c_seq[t + 1]), L.ptr(self.h_seq[t + 1]), L.ptr(None if ms is None else ms[t + 1])
             a.act_in, a.v = L.ptr(kw['act']), L.ptr(kw['v'])

@@ -45,7 +45,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__pcsamp_warps_issue_stalled_not_selected', 'smsp__pcsamp_warps_issue_stalled_selected',
         'smsp__pcsamp_warps_issue_stalled_wait', 'smsp__pcsamp_warps_issue_stalled_mio_throttle']
 traffic = {}
-for which in ('fwd', 'bwd', 'tc'):
+for which in ('fwd', 'bwd', 'tc', 'wg'):
     rep = 'gpurun_out/prof_%s_%s.ncu-rep' % (which, tag)
     if not os.path.exists(rep):
         continue
@@ -82,4 +82,7 @@ if traffic:
         old['cell_fwd_p_bytes_per_launch'] = p[0]
     if ptc:
         old['tc_cell_fwd_p_bytes_per_launch'] = ptc[0]
+    pps = [v for k, v in traffic.items() if k.startswith('tc_cell_fwd_kernel<1, 3')]      # rollout p-call that also saves
+    if pps:
+        old['tc_cell_fwd_ps_bytes_per_launch'] = pps[0]
     json.dump(old, open('profiles/traffic.json', 'w'), indent=1)
