@@ -48,7 +48,8 @@ class PolicyEngine:
         # tcgen05 path: packed 3xTF32 operands; used by the kernels when B % 128 == 0
         if use_tc is None:
             use_tc = os.environ.get('NMARL_NO_TC', '0') != '1'
-        self.use_tc = bool(use_tc) and (self.B % 128 == 0)
+        # same conditions as nmarl_tc_fwd_supported / the bptt dispatch (csrc): whole 128-env tiles, narrow encoders
+        self.use_tc = bool(use_tc) and (self.B % 128 == 0) and layout.kx_pad <= 32 and layout.kp_pad <= 32
         self.wpack = torch.zeros(layout.n_wp, **f32) if self.use_tc else None
         self.tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
         # tensor-core path: LSTM state (and its gradients) feature-major [N,64,B] so that lane == env accesses are
@@ -319,7 +320,8 @@ class PolicyEngine:
         self.sv_gates = z(T, N, B, 4 * NH)
         self.sv_enc = z(T, N, B, 128) if self.variant in ('ma2c_ic3', 'ma2c_dial') else None
         self.sv_dlv = z(T, N, B, 8)
-        self.sv_dz = z(T, N, B, 4 * NH)
+        # the tensor-core backward hands dz to the weight-gradient kernels as operand tiles (sv_dzT) only
+        self.sv_dz = z(4) if self.use_tc else z(T, N, B, 4 * NH)
         self.sv_dpre = z(T, N, B, 192)
         # tensor-core path: dz / encoder pre-activation gradients additionally as K-major [hi | lo] operand tiles
         ndp = {'ma2c_nc': 192, 'ia2c': 64}.get(self.variant, 128)
