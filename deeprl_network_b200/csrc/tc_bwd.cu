@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         for (int j = 0; j < EW; ++j) {
           const uint32_t off = tc::sw128_offset((uint32_t)(g * NH + e0 + j), (uint32_t)lane);
           const float hi = __uint_as_float(__float_as_uint(dz[j]) & 0xFFFFE000u);
-          *reinterpret_cast<float*>(tile + off) = hi;
-          *reinterpret_cast<float*>(tile + 256 * 128 + off) = dz[j] - hi;
+          __stcs(reinterpret_cast<float*>(tile + off), hi);                       // read once, by the wgrad kernel
+          __stcs(reinterpret_cast<float*>(tile + 256 * 128 + off), dz[j] - hi);
         }
       }
       produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       for (int j = 0; j < EW; ++j) {
         const uint32_t off = tc::sw128_offset((uint32_t)(n0 + j), (uint32_t)lane);
         const float hi = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
-        *reinterpret_cast<float*>(dptile + off) = hi;
-        *reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off) = vals[j] - hi;
+        __stcs(reinterpret_cast<float*>(dptile + off), hi);
+        __stcs(reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off), vals[j] - hi);
       }
     };
 #pragma unroll

@@ -100,13 +100,15 @@ __device__ __forceinline__ void enc_load(RowCtx& c, uint32_t col, float (&v)[EW]
 // 128-byte line (the row-major form would touch 32 lines per access)
 template <int NV>
 __device__ __forceinline__ void st_fm(float* base, int f0, int B, int b, const float (&v)[NV]) {
+  // saved activations are written once and read once much later (BPTT): streaming stores keep them from
+  // evicting the weights and the recurrent state the next calls re-read from L2
 #pragma unroll
-  for (int j = 0; j < NV; ++j) base[(size_t)(f0 + j) * B + b] = v[j];
+  for (int j = 0; j < NV; ++j) __stcs(base + (size_t)(f0 + j) * B + b, v[j]);
 }
 template <int NV>
 __device__ __forceinline__ void ld_fm(const float* base, int f0, int B, int b, float (&v)[NV]) {
 #pragma unroll
-  for (int j = 0; j < NV; ++j) v[j] = base[(size_t)(f0 + j) * B + b];
+  for (int j = 0; j < NV; ++j) v[j] = __ldcs(base + (size_t)(f0 + j) * B + b);
 }
 // state tensors (h, c, messages and their gradients): plane p of [planes][B][64] (env-major, FM = false) or
 // [planes][64][B] (feature-major, FM = true: lane == env row -> one 128-byte line per warp access)

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * W;
 #pragma unroll
         for (int p = 0; p < W / 4; ++p) {
-          const float4 v = *reinterpret_cast<const float4*>(src + 4 * p);
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(src + 4 * p));
           x[4 * p] = v.x; x[4 * p + 1] = v.y; x[4 * p + 2] = v.z; x[4 * p + 3] = v.w;
         }
       } else {
