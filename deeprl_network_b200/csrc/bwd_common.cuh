@@ -25,4 +25,4 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m);
 int nmarl_tc_ndp(const nmarl_model* m);
 // all GEMM weight gradients (gate + encoders) of the tensor-core path; activations are feature-major
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
-                           const float* dpT, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias);
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias);

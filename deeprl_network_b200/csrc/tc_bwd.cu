@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           dz[j] = dh[j] * tcv * go[j] * (1.0f - go[j]);
         }
       }
-      if (k.dzT == nullptr) st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);     // only needed without the tensor-core wgrad
+      st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);              // feature-major copy for the gate-bias column sums
       if (k.dzT != nullptr) {                 // dz^T tile for the tensor-core wgrad: K-major over rows, hi | lo
         uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * 256 * 128);
 #pragma unroll

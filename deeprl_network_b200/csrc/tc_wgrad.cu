@@ -8,7 +8,7 @@
 //              128B-swizzled tiles (dz: 256 rows, encoder pre-activation grads: 192/128/64 rows); the producer
 //              bulk-copies the needed row range of the tile per 32 env rows.
 //   Biases:    the obs-encoder job carries an extra all-ones lane and spans every column of the dpre tile, which
-//              yields all encoder bias gradients for free; the gate bias is a column sum over the dz^T tiles.
+//              yields all encoder bias gradients for free; the gate bias is a coalesced column sum of dz.
 #include "bwd_common.cuh"
 #include "tc_row.cuh"
 
@@ -196,38 +196,24 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
   }
 }
 
-// gate bias gradient = column sums of dz, read back from the [hi | lo] operand tiles the backward kernel wrote
-// for the GEMM jobs (dz = hi + lo exactly; the 128B swizzle only permutes a row's 16-byte chunks, which a row
-// sum does not see).  Thread = gate column: per 32-env tile it reads its 128-byte hi row and lo row, so a warp
-// covers 4 KB contiguous.  Fixed chunking + fixed-order second pass -> run-to-run deterministic.
-constexpr int COLSUM_CHUNKS = 74;
-__global__ void __launch_bounds__(NG) dzT_colsum_kernel(const float* __restrict__ dzT, int n_agents, int n_tiles_t, int T,
-                                                        float* __restrict__ part) {
-  const int ch = blockIdx.x, i = blockIdx.y, n = threadIdx.x;
-  const int total = T * n_tiles_t;                                    // 32-env tiles of this agent
-  const int per = (total + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
-  const int q0 = ch * per, q1 = min(total, q0 + per);
+// gate bias gradient: column sums of the feature-major dz (one CTA per (agent, gate column); coalesced)
+__global__ void __launch_bounds__(256) dz_colsum_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ dz,
+                                                       int B, int T, float* __restrict__ grads) {
+  __shared__ float red[8];
+  const int n = blockIdx.x, i = blockIdx.y;
   float s = 0.f;
-  for (int q = q0; q < q1; ++q) {
-    const int t = q / n_tiles_t, rb = q - t * n_tiles_t;
-    const float4* hi = reinterpret_cast<const float4*>(dzT + (((size_t)t * n_agents + i) * n_tiles_t + rb) * (size_t)(2 * NG * 32) + (size_t)n * 32);
-    const float4* lo = hi + NG * 32 / 4;
-    float a = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 h = __ldg(hi + c), l = __ldg(lo + c);
-      a += ((h.x + l.x) + (h.y + l.y)) + ((h.z + l.z) + (h.w + l.w));
-    }
-    s += a;
+  for (int t = 0; t < T; ++t) {
+    const float* p = dz + (((size_t)t * m.n_agent + i) * NG + n) * B;
+    for (int b = threadIdx.x; b < B; b += 256) s += __ldcs(p + b);
   }
-  part[((size_t)ch * n_agents + i) * NG + n] = s;
-}
-__global__ void __launch_bounds__(NG) dzT_colsum_reduce_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ part,
-                                                               float* __restrict__ grads) {
-  const int i = blockIdx.x, n = threadIdx.x;
-  float s = 0.f;
-  for (int ch = 0; ch < COLSUM_CHUNKS; ++ch) s += part[((size_t)ch * m.n_agent + i) * NG + n];
-  grads[m.agent[i].o_b + n] = s;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int w = 0; w < 8; ++w) tsum += red[w];
+    grads[m.agent[i].o_b + n] = tsum;
+  }
 }
 
 int job_list(const nmarl_model* m, int* jobs) {
@@ -263,11 +249,12 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
   const int nj = job_list(m, jobs);
   int64_t tot = 0;
   for (int j = 0; j < nj; ++j) tot += (int64_t)nmarl_tc_wgrad_splits(m->n_agent) * m->n_agent * 128 * job_N(m, jobs[j]);
-  return tot + (int64_t)COLSUM_CHUNKS * m->n_agent * NG;               // + gate-bias column-sum partials
+  return tot;
 }
 
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
-                           const float* dpT, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias) {
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st,
+                           cudaStream_t st_bias) {
   TcWgK k{};
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
@@ -279,10 +266,7 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
     NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
-  float* colsum_part = ws + off;                                       // behind the GEMM partials (nmarl_tc_wgrad_ws_floats)
-  dzT_colsum_kernel<<<dim3(COLSUM_CHUNKS, m->n_agent), NG, 0, st_bias>>>(dzT, m->n_agent, B / 32, T, colsum_part);   // beside the GEMM jobs
-  NMARL_LAUNCH_CHECK();
-  dzT_colsum_reduce_kernel<<<m->n_agent, NG, 0, st_bias>>>(*m, colsum_part, grads);
+  dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B, T, grads);   // independent of the GEMM jobs
   NMARL_LAUNCH_CHECK();
   tc_wgrad_kernel<<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();

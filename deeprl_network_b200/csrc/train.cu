@@ -947,10 +947,10 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   if (tc_wg) {
     NMARL_CHECK(a->sv_dzT && a->sv_dpT, "a2c_bptt: tensor-core path needs sv_dzT / sv_dpT");
     NMARL_CHECK(nmarl_tc_wgrad_ws_floats(m) <= a->ws_floats, "tc wgrad: workspace too small");
-    // the gate-bias column sums only read the dz^T tiles: second fork, beside the GEMM jobs
+    // the gate-bias column sums only read sv_dz: second fork, beside the GEMM jobs
     NMARL_CUDA(cudaEventRecord(ev_fork, st));
     NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->ws, a->grads, a->tc_err, st, side)) return 1;
+    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side)) return 1;
     NMARL_CUDA(cudaEventRecord(ev_join, side));
     NMARL_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     NMARL_DBG_SYNC(st, "tc_wgrads");
