@@ -874,13 +874,21 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   // 1b. policy/value head weight gradients need only sv_dlv and h_seq: they run on a forked stream
   //     beside the BPTT chain (whose 256-CTA launches leave SMs idle in their second wave) and join
   //     before the weight-gradient phase, which shares the workspace.
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (!side) {
-    NMARL_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    NMARL_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    NMARL_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  //     The helper stream and its two events are the library's only process-level state: created lazily,
+  //     once per device, by the first (un-captured) call; one host thread per device is assumed.
+  struct Fork { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+  static Fork forks[64];
+  int dev = 0;
+  NMARL_CUDA(cudaGetDevice(&dev));
+  NMARL_CHECK(dev >= 0 && dev < 64, "a2c_bptt: device ordinal %d out of range", dev);
+  Fork& fk = forks[dev];
+  if (!fk.side) {
+    NMARL_CUDA(cudaStreamCreateWithFlags(&fk.side, cudaStreamNonBlocking));
+    NMARL_CUDA(cudaEventCreateWithFlags(&fk.fork, cudaEventDisableTiming));
+    NMARL_CUDA(cudaEventCreateWithFlags(&fk.join, cudaEventDisableTiming));
   }
+  cudaStream_t side = fk.side;
+  cudaEvent_t ev_fork = fk.fork, ev_join = fk.join;
   NMARL_CUDA(cudaEventRecord(ev_fork, st));
   NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   {
