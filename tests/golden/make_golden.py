@@ -58,7 +58,7 @@ def _actions(kind, T, n, seed=0):
     raise ValueError(kind)
 
 
-def env_case(CACCEnv, ini, kind, test_mode=False, n_reset=1, **over):
+def env_case(CACCEnv, ini, kind, test_mode=False, n_reset=1, fp_seed=None, **over):
     cp = _cfg(ini, **over)
     env = CACCEnv(cp['ENV_CONFIG'])
     eps = []
@@ -76,9 +76,15 @@ def env_case(CACCEnv, ini, kind, test_mode=False, n_reset=1, **over):
         v0 = np.array(env.vs_cur, dtype=np.float64)
         acts = _actions(kind, env.T, env.n_agent, seed=100 + ep)
         obs = [np.concatenate([np.asarray(o, dtype=np.float64) for o in ob])]
-        rews, dones, greps, hs, vs, us = [], [], [], [], [], []
+        rews, dones, greps, hs, vs, us, fps = [], [], [], [], [], [], []
         nstep = 0
+        fp_rs = None if fp_seed is None else np.random.RandomState(fp_seed + ep)
         for t in range(env.T):
+            if fp_rs is not None:
+                # what Trainer.explore does before every step (utils.py:173): fingerprints = the policies just computed
+                fp = fp_rs.dirichlet(np.ones(env.n_a), size=env.n_agent)
+                env.update_fingerprint(fp)
+                fps.append(fp)
             ob, r, d, g = env.step(acts[t])
             obs.append(np.concatenate([np.asarray(o, dtype=np.float64) for o in ob]))
             rews.append(np.broadcast_to(np.asarray(r, dtype=np.float64), (env.n_agent,)).copy())
@@ -91,7 +97,7 @@ def env_case(CACCEnv, ini, kind, test_mode=False, n_reset=1, **over):
         eps.append(dict(h0=h0, v0=v0, seed_after=seed_after, acts=acts[:nstep], obs=np.array(obs),
                         rew=np.array(rews), done=np.array(dones), greward=np.array(greps),
                         hs=np.array(hs), vs=np.array(vs), us=np.array(us),
-                        v0s=np.array(env.v0s)))
+                        v0s=np.array(env.v0s), **({} if fp_rs is None else dict(fps=np.array(fps)))))
     out = {}
     for k, ep in enumerate(eps):
         for key, val in ep.items():
@@ -190,10 +196,20 @@ def main():
         #  cacc_env.py:290/311 -- is rejected by np.random.seed in __init__: dead code)
         ('env_nc_catchup_seed0', ('config_ma2c_nc_catchup.ini', 'const3'), dict(seed=0)),
     ]
+    # fingerprint-carrying observations (ia2c_fp) and the remaining CACC configs; replayed by the CPU oracle test only
+    cases += [
+        ('envfp_ia2c_fp_catchup_rand', ('config_ia2c_fp_catchup.ini', 'rand'), dict(fp_seed=7)),
+        ('envfp_ia2c_fp_slowdown_cyc', ('config_ia2c_fp_slowdown.ini', 'cyc'), dict(fp_seed=8, n_reset=2)),
+        ('envfp_ma2c_cu_catchup_rand', ('config_ia2c_cu_catchup.ini', 'rand'), dict(fp_seed=9)),
+    ]
     for name, (ini, kind), kw in cases:
+        if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
+            continue
         out = env_case(CACCEnv, ini, kind, **kw)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'steps', len(out['ep0_done']), 'sumG', float(np.sum(out['ep0_greward'])))
+    if '--force' not in sys.argv:
+        return
     for name, alpha, multi in [('buffer_ma_global', -1, True), ('buffer_ma_spatial09', 0.9, True),
                                ('buffer_ia_global', -1, False), ('buffer_ia_spatial08', 0.8, False)]:
         out = buffer_case(au, alpha, multi)

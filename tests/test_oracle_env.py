@@ -10,6 +10,8 @@ from helpers import GOLDEN, ROOT, load_cfg
 from oracle.cacc import OracleCACC, leader_speed, np_pairwise_sum
 
 FILES = sorted(glob.glob(os.path.join(GOLDEN, 'env_*.npz')))
+# ia2c_fp / ma2c_cu trajectories with the fingerprints the trainer would set before every step
+FP_FILES = sorted(glob.glob(os.path.join(GOLDEN, 'envfp_*.npz')))
 
 
 def _run(g):
@@ -27,7 +29,10 @@ def _run(g):
         np.testing.assert_array_equal(env.vs_cur, g['ep%d_v0' % ep])
         obs = [np.concatenate(ob)]
         acts = g['ep%d_acts' % ep]
+        fps = g['ep%d_fps' % ep] if ('ep%d_fps' % ep) in g.files else None
         for t in range(len(acts)):
+            if fps is not None:
+                env.update_fingerprint(fps[t])
             ob, r, d, gr = env.step(acts[t])
             obs.append(np.concatenate(ob))
             assert gr == g['ep%d_greward' % ep][t]
@@ -38,9 +43,9 @@ def _run(g):
         yield env, g, ep
 
 
-@pytest.mark.parametrize('path', FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+@pytest.mark.parametrize('path', FILES + FP_FILES, ids=[os.path.basename(f)[:-4] for f in FILES + FP_FILES])
 def test_oracle_matches_reference_trajectory(path):
-    assert len(FILES) >= 10
+    assert len(FILES) >= 10 and len(FP_FILES) == 3
     g = np.load(path, allow_pickle=True)
     for _ in _run(g):
         pass
@@ -86,3 +91,15 @@ def test_ia2c_observation_is_own_plus_neighbours():
     env2 = OracleCACC(cp2['ENV_CONFIG'])
     ob2 = env2.reset()
     np.testing.assert_array_equal(ob[3], np.concatenate([ob2[3], ob2[2], ob2[4]]))
+
+
+def test_fingerprints_sit_at_the_end_of_the_ia2c_fp_observation():
+    """envs/cacc_env.py:74-77 on the reference's own trajectory: [own 5 | neighbours 5 each | fingerprints 4 each]."""
+    g = np.load(os.path.join(GOLDEN, 'envfp_ia2c_fp_catchup_rand.npz'), allow_pickle=True)
+    obs, fps = g['ep0_obs'], g['ep0_fps']
+    widths = [5 * 2 + 4, 5 * 3 + 8, 5 * 3 + 8, 5 * 3 + 8, 5 * 3 + 8, 5 * 3 + 8, 5 * 3 + 8, 5 * 2 + 4]
+    assert obs.shape[1] == sum(widths)
+    np.testing.assert_array_equal(obs[0][10:14], np.full(4, 0.25))            # reset: uniform fingerprint of agent 1
+    o3 = obs[5][sum(widths[:3]):sum(widths[:4])]                               # agent 3 after 5 steps: neighbours 2 and 4
+    np.testing.assert_array_equal(o3[15:19], fps[4][2])
+    np.testing.assert_array_equal(o3[19:23], fps[4][4])
