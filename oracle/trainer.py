@@ -1,7 +1,9 @@
 """CPU oracle: agent wrappers + the rollout/train loop, B=1, with the reference's quirks.
 
 TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  PARITY UNPINNED for the parts that
-sit on TensorFlow (see oracle/nets.py); the control flow follows
+sit on TensorFlow (see oracle/nets.py).  The rollout CONTROL FLOW (``OracleTrainer``, ``Counter``) is PINNED:
+tests/test_trainer_flow.py replays traces recorded from the unmodified reference ``utils.Trainer`` driving a
+scripted agent (tests/golden/trainer_*.npz) bit for bit.  It follows
 
   * ``IA2C`` / ``MA2C_*`` wrappers  agents/models.py:26-51, 198-227, 134-158, 246-258
   * ``Trainer._get_policy/_get_value/explore/perform/run``  utils.py:129-254

@@ -171,6 +171,30 @@ def eval_case(CACCEnv, ini, kind, out_prefix):
     return acts[:t + 1]
 
 
+def trainer_case(CACCEnv, ini, total_step):
+    """The UNMODIFIED reference Trainer + Counter + CACCEnv driving a scripted agent (tests/helpers.py
+    ScriptedAgent): the trace of every agent call pins the rollout control flow (utils.py:129-254, quirks Q1-Q6)."""
+    import tempfile
+    tf = sys.modules['tensorflow']
+    tf.float32 = 'float32'
+    tf.placeholder = lambda *a, **k: object()
+    tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: object())
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import ScriptedAgent
+    import utils as ref_utils
+    cp = _cfg(ini)
+    env = CACCEnv(cp['ENV_CONFIG'])
+    agent = ScriptedAgent(env.agent, env.n_agent, env.n_a, cp['MODEL_CONFIG'].getint('batch_size'))
+    writer = types.SimpleNamespace(add_summary=lambda *a, **k: None, flush=lambda: None)
+    counter = ref_utils.Counter(total_step, 10 ** 9, 10 ** 9)
+    out_dir = tempfile.mkdtemp() + '/'
+    tr = ref_utils.Trainer(env, agent, counter, writer, output_path=out_dir)
+    tr.run()
+    data = np.array([[d['step'], d['avg_reward'], d['std_reward']] for d in tr.data])
+    return dict(trace=np.array(agent.trace), data=data, seed_after=env.seed, cur_step=counter.cur_step,
+                ini=ini, total_step=total_step)
+
+
 def scheduler_case(au):
     s1 = au.Scheduler(5e-4, decay='constant')
     s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
@@ -208,6 +232,14 @@ def main():
         out = env_case(CACCEnv, ini, kind, **kw)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'steps', len(out['ep0_done']), 'sumG', float(np.sum(out['ep0_greward'])))
+    for name, ini, total in [('trainer_ma2c_nc_catchup', 'config_ma2c_nc_catchup.ini', 700),
+                             ('trainer_ia2c_slowdown', 'config_ia2c_slowdown.ini', 700),
+                             ('trainer_ia2c_fp_catchup', 'config_ia2c_fp_catchup.ini', 300)]:
+        if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
+            continue
+        out = trainer_case(CACCEnv, ini, total)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'])
     if '--force' not in sys.argv:
         return
     for name, alpha, multi in [('buffer_ma_global', -1, True), ('buffer_ma_spatial09', 0.9, True),
