@@ -195,6 +195,94 @@ def trainer_case(CACCEnv, ini, total_step):
                 ini=ini, total_step=total_step)
 
 
+def agent_case(CACCEnv, ini, total_step):
+    """The UNMODIFIED reference agent class (IA2C / IA2C_FP / MA2C_*: reward scaling, buffers, returns, lr schedule,
+    argument marshalling -- agents/models.py) inside the reference Trainer, with only the TF policy objects replaced
+    by scripted ones that record what they are called with (helpers.PolicyTrace): pins everything up to the TF
+    boundary."""
+    import tempfile
+    from unittest.mock import MagicMock
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import PolicyTrace, script_pi, script_v
+    tf = MagicMock()
+    sys.modules['tensorflow'] = tf
+    for mod in ('agents.models', 'utils'):
+        sys.modules.pop(mod, None)
+    import agents.models as am
+    import utils as ref_utils
+    ref_utils.tf = tf
+    cp = _cfg(ini)
+    env = CACCEnv(cp['ENV_CONFIG'])
+    tr = PolicyTrace(env.n_agent, env.n_a)
+    nbr = [np.where(env.neighbor_mask[i] == 1)[0] for i in range(env.n_agent)]
+
+    class SinglePolicy:                       # LstmPolicy / FPPolicy stand-in (one per agent)
+        def __init__(self, n_s, n_a, n_n, n_step, n_fc=64, n_lstm=64, name=None, **kw):
+            self.i, self.k = int(name), 0
+
+        def prepare_loss(self, *a, **k):
+            pass
+
+        def _reset(self):
+            tr.rec(1, self.i)
+            self.k = 0
+
+        def forward(self, sess, ob, done, naction=None, out_type='p'):
+            own = np.asarray(ob, dtype=np.float64)[None, :5]
+            if out_type.startswith('p'):
+                self.k += 1
+                pi = script_pi(own, self.k, done, tr.w[self.i:self.i + 1])[0]
+                tr.rec(2, self.i, float(bool(done)), np.asarray(ob, dtype=np.float32), pi)
+                return pi
+            v = script_v(own, self.k)[0]
+            tr.rec(3, self.i, float(bool(done)), naction, v)
+            return v
+
+        def backward(self, sess, obs, nas, acts, dones, Rs, Advs, cur_lr, summary_writer=None, global_step=None):
+            tr.rec(5, self.i, cur_lr, obs, nas, acts, dones, Rs, Advs)
+
+    class MultiPolicy:                        # NC / IC3 / DIAL multi-agent policy stand-in
+        def __init__(self, n_s, n_a, n_agent, n_step, neighbor_mask, **kw):
+            self.k = 0
+
+        def prepare_loss(self, *a, **k):
+            pass
+
+        def _reset(self):
+            tr.rec(1)
+            self.k = 0
+
+        def forward(self, sess, ob, done, policy, action=None, out_type='p'):
+            own = np.asarray(ob, dtype=np.float64)[:, :5]
+            if out_type.startswith('p'):
+                self.k += 1
+                pi = script_pi(own, self.k, done, tr.w)
+                tr.rec(2, float(bool(done)), np.asarray(ob, dtype=np.float32), np.asarray(policy, dtype=np.float32), pi)
+                return pi
+            v = script_v(own, self.k)
+            tr.rec(3, float(bool(done)), action, v)
+            return v
+
+        def backward(self, sess, obs, ps, acts, dones, Rs, Advs, cur_lr, summary_writer=None, global_step=None):
+            # reference layout [N,T,..] -> canonical [T,N,..]
+            tr.rec(5, cur_lr, np.transpose(obs, (1, 0, 2)), np.transpose(ps, (1, 0, 2)), np.transpose(acts), dones,
+                   np.transpose(Rs), np.transpose(Advs))
+
+    am.LstmPolicy = am.FPPolicy = SinglePolicy
+    am.NCMultiAgentPolicy = am.IC3MultiAgentPolicy = am.DIALMultiAgentPolicy = MultiPolicy
+    cls = {'ia2c': am.IA2C, 'ia2c_fp': am.IA2C_FP, 'ma2c_nc': am.MA2C_NC, 'ma2c_ic3': am.MA2C_IC3,
+           'ma2c_dial': am.MA2C_DIAL}[env.agent]
+    model = cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma, 10 ** 6,
+                cp['MODEL_CONFIG'], seed=12)
+    writer = types.SimpleNamespace(add_summary=lambda *a, **k: None, flush=lambda: None)
+    counter = ref_utils.Counter(total_step, 10 ** 9, 10 ** 9)
+    trainer = ref_utils.Trainer(env, model, counter, writer, output_path=tempfile.mkdtemp() + '/')
+    trainer.run()
+    data = np.array([[d['step'], d['avg_reward'], d['std_reward']] for d in trainer.data])
+    return dict(trace=np.array(tr.t), data=data, seed_after=env.seed, cur_step=counter.cur_step, ini=ini,
+                total_step=total_step)
+
+
 def scheduler_case(au):
     s1 = au.Scheduler(5e-4, decay='constant')
     s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
@@ -238,6 +326,16 @@ def main():
         if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
             continue
         out = trainer_case(CACCEnv, ini, total)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'])
+    for name, ini, total in [('agent_ma2c_nc_catchup', 'config_ma2c_nc_catchup.ini', 300),
+                             ('agent_ia2c_slowdown', 'config_ia2c_slowdown.ini', 300),
+                             ('agent_ia2c_fp_slowdown', 'config_ia2c_fp_slowdown.ini', 200),
+                             ('agent_ma2c_ic3_slowdown', 'config_ma2c_cnet_slowdown.ini', 200),
+                             ('agent_ma2c_dial_catchup', 'config_ma2c_dial_catchup.ini', 200)]:
+        if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
+            continue
+        out = agent_case(CACCEnv, ini, total)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'])
     if '--force' not in sys.argv:

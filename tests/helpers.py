@@ -87,3 +87,28 @@ class ScriptedAgent:
     def backward(self, Rends, dt=0, summary_writer=None, global_step=None):
         self._rec(5, Rends, dt)
         return {}
+
+
+# ---- scripted POLICY level (one step below ScriptedAgent): pins the agent classes' host logic ------------------
+def script_pi(own, k, done, w):
+    """own [n,5] float64 -> pi [n, n_a]; k = policy calls since reset (stand-in for the recurrent state)."""
+    z = np.einsum('if,ifa->ia', own, w) + 0.05 * k - 0.5 * float(bool(done))
+    e = np.exp(z - z.max(1, keepdims=True))
+    return e / e.sum(1, keepdims=True)
+
+
+def script_v(own, k):
+    return own.sum(1) * 0.01 + 0.1 * k
+
+
+class PolicyTrace:
+    """Canonical record of what crosses the agent -> policy boundary (the TF boundary in the reference)."""
+
+    def __init__(self, n_agent, n_a):
+        self.t = []
+        self.w = np.random.RandomState(4321).randn(n_agent, 5, n_a)
+
+    def rec(self, code, *parts):
+        self.t.append(float(code))
+        for p in parts:
+            self.t.extend(np.asarray(p, dtype=np.float64).ravel().tolist())
