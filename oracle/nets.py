@@ -2,8 +2,11 @@
 restated in PyTorch-CPU (fp32 by default, fp64 switch).
 
 TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.
-PARITY UNPINNED: TensorFlow 1.12 (README.md:23) cannot be installed here and the
-reference has no tests at this boundary; this file is a line-by-line restatement of
+PINNED to the reference's own network source executed on a TF shim (tests/golden/tf_shim.py,
+tests/test_tfnet_parity.py: pi / v / R within 2e-7 and trained weights within 3e-8 of the unmodified
+reference code for all six agents); TensorFlow 1.12 (README.md:23) itself cannot be installed here, so the
+TF primitives' own semantics (incl. the clip / RMSProp formulas below) remain restated, not measured.
+This file is a line-by-line restatement of
 
   * ``fc``            agents/utils.py:65-73        * ``ortho_init``  agents/utils.py:10-23
   * ``lstm``          agents/utils.py:87-115       (IA2C / LstmPolicy, policies.py:136-149)

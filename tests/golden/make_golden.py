@@ -12,6 +12,7 @@ Reference pieces executed here:
      as a default argument at import time -- SURVEY 8c)
 """
 import configparser
+import hashlib
 import os
 import sys
 import types
@@ -283,6 +284,55 @@ def agent_case(CACCEnv, ini, total_step):
                 total_step=total_step)
 
 
+def tfnet_case(ini, total_step):
+    """The UNMODIFIED reference end to end -- env, Trainer, agent class, policy classes and layer functions -- with
+    TensorFlow replaced by tests/golden/tf_shim.py (the TF primitives restated on PyTorch-CPU).  Records the initial
+    weights (reference variable names), every pi / v / bootstrap R the Trainer saw, and the weights after training."""
+    import importlib
+    import tempfile
+    sys.setrecursionlimit(100000)
+    sys.path.insert(0, HERE)
+    tf = importlib.import_module('tf_shim')
+    sys.modules['tensorflow'] = tf
+    for mod in ('agents.models', 'agents.policies', 'agents.utils', 'utils', 'envs.cacc_env'):
+        sys.modules.pop(mod, None)
+    from envs.cacc_env import CACCEnv
+    import agents.models as am
+    import utils as ref_utils
+    cp = _cfg(ini)
+    env = CACCEnv(cp['ENV_CONFIG'])
+    cls = {'ia2c': am.IA2C, 'ia2c_fp': am.IA2C_FP, 'ma2c_nc': am.MA2C_NC, 'ma2c_ic3': am.MA2C_IC3,
+           'ma2c_dial': am.MA2C_DIAL, 'ma2c_cu': am.IA2C_CU}[env.agent]
+    model = cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma, 10 ** 6,
+                cp['MODEL_CONFIG'], seed=12)
+    w0 = tf.variable_values()
+    log = []
+
+    class Rec:
+        def __getattr__(self, k):
+            return getattr(model, k)
+
+        def forward(self, *a, **k):
+            out = model.forward(*a, **k)
+            log.append(np.array(out, dtype=np.float64).ravel())
+            return out
+
+        def backward(self, R, *a, **k):
+            log.append(np.asarray(R, dtype=np.float64).ravel())
+            return model.backward(R, *a, **k)
+    writer = types.SimpleNamespace(add_summary=lambda *a, **k: None, flush=lambda: None)
+    counter = ref_utils.Counter(total_step, 10 ** 9, 10 ** 9)
+    trainer = ref_utils.Trainer(env, Rec(), counter, writer, output_path=tempfile.mkdtemp() + '/')
+    trainer.run()
+    w1 = tf.variable_values()
+    out = dict(trace=np.concatenate(log), data=np.array([[d['step'], d['avg_reward'], d['std_reward']] for d in trainer.data]),
+               seed_after=env.seed, cur_step=counter.cur_step, ini=ini, total_step=total_step, names=np.array(list(w0)))
+    for n in w0:
+        out['w0sha/' + n] = hashlib.sha256(np.ascontiguousarray(w0[n]).tobytes()).hexdigest()   # exact-match check only
+        out['w1/' + n] = w1[n]
+    return out
+
+
 def scheduler_case(au):
     s1 = au.Scheduler(5e-4, decay='constant')
     s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
@@ -328,6 +378,18 @@ def main():
         out = trainer_case(CACCEnv, ini, total)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'])
+    for name, ini, total in [('tfnet_ma2c_nc_catchup', 'config_ma2c_nc_catchup.ini', 300),
+                             ('tfnet_ia2c_slowdown', 'config_ia2c_slowdown.ini', 100),
+                             ('tfnet_ia2c_fp_catchup', 'config_ia2c_fp_catchup.ini', 100),
+                             ('tfnet_ma2c_ic3_slowdown', 'config_ma2c_cnet_slowdown.ini', 100),
+                             ('tfnet_ma2c_dial_catchup', 'config_ma2c_dial_catchup.ini', 100),
+                             ('tfnet_ma2c_cu_catchup', 'config_ia2c_cu_catchup.ini', 100)]:
+        if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
+            continue
+        out = tfnet_case(ini, total)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'],
+              'n_var', len(out['names']))
     for name, ini, total in [('agent_ma2c_nc_catchup', 'config_ma2c_nc_catchup.ini', 300),
                              ('agent_ia2c_slowdown', 'config_ia2c_slowdown.ini', 300),
                              ('agent_ia2c_fp_slowdown', 'config_ia2c_fp_slowdown.ini', 200),
