@@ -1,26 +1,31 @@
-"""Rollout / train loop and experiment plumbing -- mirror of the reference's utils.py.
+"""Experiment plumbing and the two training loops.
 
-``Counter``, ``Trainer`` (``explore`` / ``perform`` / ``run``), ``Evaluator`` and the directory /
-logging helpers keep the reference's names, arguments and control flow (utils.py:11-60, 70-97,
-100-254, 311-336), including its quirks: the value call after the policy
-call, the state-advancing bootstrap, the interleaved greedy test episode for CACC whose
-reward is what gets logged, and the counter that only counts training steps.
+Drop-in surface (names, arguments and observable behaviour of the reference's utils.py:11-60, 70-97, 100-254,
+311-336): ``Counter``, ``Trainer`` with ``explore`` / ``perform`` / ``run``, ``Tester``, ``Evaluator`` and the
+directory / logging helpers.  The single-environment ``Trainer`` reproduces the reference loop call for call --
+tests/test_trainer_flow.py replays traces recorded from the reference's own Trainer bit for bit -- including
+its quirks: Q1 the value call follows the policy call on the already advanced recurrent state, Q2 the
+bootstrap at a non-terminal batch end is one more policy + value call, Q4 the reward that gets logged for CACC is
+that of a greedy test episode run after every training episode, Q5 only training steps are counted.
 
-``VecTrainer`` is the new batched loop (n_env parallel episodes, everything device resident,
+``VecTrainer`` is the batched loop this package adds (n_env parallel episodes, everything device resident,
 optionally one process per GPU with one NCCL gradient all-reduce per update).
 """
-import itertools
 import logging
-import os
+import pathlib
 import shutil
 import time
 
 import numpy as np
 import torch
 
+_TEST_MODES = {'no_test': (False, False), 'in_train_test': (True, False),
+               'after_train_test': (False, True), 'all_test': (True, True)}
 
+
+# ---- directories / logging ---------------------------------------------------------------------------------------
 def check_dir(cur_dir):
-    return os.path.exists(cur_dir)
+    return pathlib.Path(cur_dir).exists()
 
 
 def copy_file(src_dir, tar_dir):
@@ -28,37 +33,36 @@ def copy_file(src_dir, tar_dir):
 
 
 def find_file(cur_dir, suffix='.ini'):
-    for file in os.listdir(cur_dir):
-        if file.endswith(suffix):
-            return cur_dir + '/' + file
+    root = pathlib.Path(cur_dir)
+    hits = sorted(f for f in root.iterdir() if f.name.endswith(suffix)) if root.is_dir() else []
+    if hits:
+        return '%s/%s' % (cur_dir, hits[0].name)
     logging.error('Cannot find %s file' % suffix)
     return None
 
 
-def init_dir(base_dir, pathes=['log', 'data', 'model']):
-    if not os.path.exists(base_dir):
-        os.mkdir(base_dir)
-    dirs = {}
-    for path in pathes:
-        cur_dir = base_dir + '/%s/' % path
-        if not os.path.exists(cur_dir):
-            os.mkdir(cur_dir)
-        dirs[path] = cur_dir
-    return dirs
+def init_dir(base_dir, pathes=('log', 'data', 'model')):
+    """-> {'log': '<base>/log/', ...}; creates what is missing."""
+    out = {}
+    for sub in pathes:
+        d = pathlib.Path(base_dir) / sub
+        d.mkdir(parents=True, exist_ok=True)
+        out[sub] = '%s/%s/' % (base_dir, sub)
+    return out
 
 
 def init_log(log_dir):
+    stamp = int(time.time())
     logging.basicConfig(format='%(asctime)s [%(levelname)s] %(message)s', level=logging.INFO,
-                        handlers=[logging.FileHandler('%s/%d.log' % (log_dir, time.time())), logging.StreamHandler()])
+                        handlers=[logging.FileHandler('%s/%d.log' % (log_dir, stamp)), logging.StreamHandler()])
 
 
 def init_test_flag(test_mode):
-    return {'no_test': (False, False), 'in_train_test': (True, False), 'after_train_test': (False, True),
-            'all_test': (True, True)}.get(test_mode, (False, False))
+    return _TEST_MODES.get(test_mode, (False, False))
 
 
 def make_summary_writer(log_dir):
-    """TensorBoard event writer (replaces tf.summary.FileWriter); None if tensorboard is absent."""
+    """TensorBoard event writer (stands in for tf.summary.FileWriter); None when tensorboard is absent."""
     try:
         from torch.utils.tensorboard import SummaryWriter
         return SummaryWriter(log_dir)
@@ -68,199 +72,191 @@ def make_summary_writer(log_dir):
 
 
 class Counter:
-    """utils.py:70-97"""
+    """Global step bookkeeping: counts training steps only; test / log cadence; stop condition."""
 
     def __init__(self, total_step, test_step, log_step):
-        self.counter = itertools.count(1)
-        self.cur_step = 0
-        self.cur_test_step = 0
-        self.total_step = total_step
-        self.test_step = test_step
-        self.log_step = log_step
+        self.total_step, self.test_step, self.log_step = total_step, test_step, log_step
+        self.cur_step = self.cur_test_step = 0
         self.stop = False
 
     def next(self):
-        self.cur_step = next(self.counter)
+        self.cur_step += 1
         return self.cur_step
 
     def should_test(self):
-        test = False
-        if (self.cur_step - self.cur_test_step) >= self.test_step:
-            test = True
+        due = self.cur_step - self.cur_test_step >= self.test_step
+        if due:
             self.cur_test_step = self.cur_step
-        return test
+        return due
 
     def should_log(self):
         return self.cur_step % self.log_step == 0
 
     def should_stop(self):
-        if self.cur_step >= self.total_step:
-            return True
-        return self.stop
+        return self.stop or self.cur_step >= self.total_step
+
+
+# ---- the single-environment loop -----------------------------------------------------------------------------------
+class _AgentPort:
+    """The two call conventions of the agent classes behind one face.  MA2C-style agents take the whole
+    fingerprint matrix with every call and the joint action for the value; IA2C-style agents take nothing extra
+    for the policy and, per agent, its neighbours' actions for the value.  ``aux`` is whatever the last call used
+    and is what ``add_transition`` stores next to the observation."""
+
+    def __init__(self, env, model):
+        self.env, self.model = env, model
+        self.joint = env.agent.startswith('ma2c')
+        self.aux = None
+
+    def policy(self, ob, done):
+        if not self.joint:
+            return self.model.forward(ob, done)
+        self.aux = self.env.get_fingerprint()
+        return self.model.forward(ob, done, self.aux)
+
+    def value(self, ob, done, action):
+        if self.joint:
+            return self.model.forward(ob, done, self.aux, np.array(action), 'v')
+        self.aux = self.env.get_neighbor_action(action)
+        return self.model.forward(ob, done, self.aux, 'v')
+
+    def store(self, ob, action, reward, value, done):
+        self.model.add_transition(ob, self.aux, action, reward, value, done)
 
 
 class Trainer:
-    """One environment, one episode at a time, exactly like the reference (utils.py:100-254)."""
+    """One environment, one episode at a time (the reference's protocol).  ``uniform_fn`` optionally supplies the
+    uniform behind each sampled action (tests feed the CUDA path and the oracle the same stream); by default
+    actions come from ``np.random.choice`` like in the reference."""
 
     def __init__(self, env, model, global_counter, summary_writer, output_path=None, uniform_fn=None):
-        self.cur_step = 0
-        self.global_counter = global_counter
-        self.env = env
-        self.agent = self.env.agent
-        self.model = model
+        self.env, self.model, self.global_counter = env, model, global_counter
+        self.summary_writer, self.output_path, self.uniform_fn = summary_writer, output_path, uniform_fn
+        self.agent = env.agent
         self.sess = getattr(model, 'sess', None)
-        self.n_step = self.model.n_step
-        self.summary_writer = summary_writer
-        assert self.env.T % self.n_step == 0
+        self.n_step = model.n_step
+        if env.T % self.n_step:
+            raise AssertionError('episode length %d is not a multiple of the batch size %d' % (env.T, self.n_step))
+        self.cur_step = 0
         self.data = []
-        self.output_path = output_path
+        self.episode_rewards = []
         self.env.train_mode = True
-        # the uniform each np.random.choice draw consumes (tests inject their own stream)
-        self.uniform_fn = uniform_fn
+        self._port = _AgentPort(env, model)
 
+    # -- action selection --
+    def _draw(self, pi):
+        if self.uniform_fn is None:
+            return np.random.choice(np.arange(len(pi)), p=pi)
+        cdf = np.cumsum(np.asarray(pi, dtype=np.float64))
+        return int(np.searchsorted(cdf / cdf[-1], self.uniform_fn(), side='right'))
+
+    def _decide(self, ob, done, greedy=False):
+        policy = self._port.policy(ob, done)
+        pick = np.argmax if greedy else self._draw
+        return policy, np.array([pick(pi) for pi in policy])
+
+    # -- logging --
     def _add_summary(self, reward, global_step, is_train=True):
         if self.summary_writer is not None:
             self.summary_writer.add_scalar('train_reward' if is_train else 'test_reward', reward, global_step)
 
-    def _sample(self, pi):
-        if self.uniform_fn is None:
-            return np.random.choice(np.arange(len(pi)), p=pi)
-        cdf = np.cumsum(np.asarray(pi, dtype=np.float64))
-        cdf /= cdf[-1]
-        return int(np.searchsorted(cdf, self.uniform_fn(), side='right'))
-
-    def _get_policy(self, ob, done, mode='train'):
-        if self.agent.startswith('ma2c'):
-            self.ps = self.env.get_fingerprint()
-            policy = self.model.forward(ob, done, self.ps)
-        else:
-            policy = self.model.forward(ob, done)
-        action = []
-        for pi in policy:
-            action.append(self._sample(pi) if mode == 'train' else np.argmax(pi))
-        return policy, np.array(action)
-
-    def _get_value(self, ob, done, action):
-        if self.agent.startswith('ma2c'):
-            return self.model.forward(ob, done, self.ps, np.array(action), 'v')
-        self.naction = self.env.get_neighbor_action(action)
-        if not self.naction:
-            self.naction = np.nan
-        return self.model.forward(ob, done, self.naction, 'v')
-
     def _log_episode(self, global_step, mean_reward, std_reward):
-        self.data.append({'agent': self.agent, 'step': global_step, 'test_id': -1,
-                          'avg_reward': mean_reward, 'std_reward': std_reward})
+        self.data.append(dict(agent=self.agent, step=global_step, test_id=-1, avg_reward=mean_reward,
+                              std_reward=std_reward))
         self._add_summary(mean_reward, global_step)
         if self.summary_writer is not None:
             self.summary_writer.flush()
 
+    # -- one batch of at most n_step transitions + its bootstrap target --
     def explore(self, prev_ob, prev_done):
-        ob, done = prev_ob, prev_done
+        ob, done, port = prev_ob, prev_done, self._port
         for _ in range(self.n_step):
-            policy, action = self._get_policy(ob, done)          # pre-decision
-            value = self._get_value(ob, done, action)            # post-decision (quirk Q1)
+            policy, action = self._decide(ob, done)
+            value = port.value(ob, done, action)                  # Q1: evaluated after the policy call
             self.env.update_fingerprint(policy)
-            next_ob, reward, done, global_reward = self.env.step(action)
+            nxt, reward, done, global_reward = self.env.step(action)
             self.episode_rewards.append(global_reward)
-            global_step = self.global_counter.next()
+            step = self.global_counter.next()
             self.cur_step += 1
-            if self.agent.startswith('ma2c'):
-                self.model.add_transition(ob, self.ps, action, reward, value, done)
-            else:
-                self.model.add_transition(ob, self.naction, action, reward, value, done)
+            port.store(ob, action, reward, value, done)
             if self.global_counter.should_log():
-                logging.info('''Training: global step %d, episode step %d,
-                                   ob: %s, a: %s, pi: %s, r: %.2f, train r: %.2f, done: %r''' %
-                             (global_step, self.cur_step, str(ob), str(action), str(policy), global_reward,
-                              np.mean(reward), done))
-            if done:                                             # terminal check inside the batch loop
-                break
-            ob = next_ob
-        if done:
-            R = np.zeros(self.model.n_agent)
-        else:                                                    # quirk Q2
-            _, action = self._get_policy(ob, done)
-            R = self._get_value(ob, done, action)
-        return ob, done, R
+                logging.info('Training: global step %d, episode step %d, ob: %s, a: %s, pi: %s, r: %.2f, '
+                             'train r: %.2f, done: %r' % (step, self.cur_step, ob, action, policy, global_reward,
+                                                          np.mean(reward), done))
+            if done:                                              # CACC episodes may end inside a batch
+                return ob, done, np.zeros(self.model.n_agent)
+            ob = nxt
+        _, action = self._decide(ob, done)                        # Q2: the bootstrap is a full policy + value call
+        return ob, done, port.value(ob, done, action)
 
+    # -- one evaluation episode --
     def perform(self, test_ind, gui=False):
-        ob = self.env.reset(gui=gui, test_ind=test_ind)
-        rewards = []
-        done = True                                              # pre-decision done resets the LSTM
+        ob, done = self.env.reset(gui=gui, test_ind=test_ind), True      # done=True clears the recurrent state
         self.model.reset()
+        greedy = not self.env.name.startswith('atsc')                    # CACC is evaluated with the arg-max policy
+        rewards = []
         while True:
-            if self.env.name.startswith('atsc'):
-                policy, action = self._get_policy(ob, done)
-            else:                                                # CACC: deterministic test policy
-                policy, action = self._get_policy(ob, done, mode='test')
+            policy, action = self._decide(ob, done, greedy=greedy)
             self.env.update_fingerprint(policy)
-            next_ob, reward, done, global_reward = self.env.step(action)
+            ob, _, done, global_reward = self.env.step(action)
             rewards.append(global_reward)
             if done:
-                break
-            ob = next_ob
-        return np.mean(np.array(rewards)), np.std(np.array(rewards))
+                rewards = np.array(rewards)
+                return np.mean(rewards), np.std(rewards)
+
+    def _train_episode(self):
+        ob, done = self.env.reset(), True
+        self.model.reset()
+        self.cur_step, self.episode_rewards = 0, []
+        while True:
+            ob, done, R = self.explore(ob, done)
+            step = self.global_counter.cur_step
+            self.model.backward(R, self.env.T - self.cur_step, self.summary_writer, step)
+            if done:
+                self.env.terminate()
+                return step
 
     def run(self, max_episodes=None):
-        n_ep = 0
-        while not self.global_counter.should_stop():
-            ob = self.env.reset()
-            done = True
-            self.model.reset()
-            self.cur_step = 0
-            self.episode_rewards = []
-            while True:
-                ob, done, R = self.explore(ob, done)
-                dt = self.env.T - self.cur_step
-                global_step = self.global_counter.cur_step
-                self.model.backward(R, dt, self.summary_writer, global_step)
-                if done:
-                    self.env.terminate()
-                    break
+        episodes = 0
+        while not self.global_counter.should_stop() and (max_episodes is None or episodes < max_episodes):
+            step = self._train_episode()
             rewards = np.array(self.episode_rewards)
             mean_reward, std_reward = np.mean(rewards), np.std(rewards)
-            if not self.env.name.startswith('atsc'):             # quirk Q4
+            if not self.env.name.startswith('atsc'):              # Q4: a greedy episode provides the logged reward
                 self.env.train_mode = False
                 mean_reward, std_reward = self.perform(-1)
                 self.env.train_mode = True
-            self._log_episode(global_step, mean_reward, std_reward)
-            n_ep += 1
-            if max_episodes is not None and n_ep >= max_episodes:
-                break
+            self._log_episode(step, mean_reward, std_reward)
+            episodes += 1
         if self.output_path is not None:
             import pandas as pd
             pd.DataFrame(self.data).to_csv(self.output_path + 'train_reward.csv')
 
 
 class Tester(Trainer):
-    """Imported by the reference's main.py but never invoked (SURVEY row 11); kept for API parity."""
+    """Present in the reference's import list but never run by its main.py; kept so that the
+    import keeps working."""
 
     def __init__(self, env, model, global_counter, summary_writer, output_path):
-        super().__init__(env, model, global_counter, summary_writer)
+        super().__init__(env, model, global_counter, summary_writer, output_path=output_path)
         self.env.train_mode = False
-        self.test_num = self.env.test_num
-        self.output_path = output_path
-        self.data = []
+        self.test_num = env.test_num
 
 
 class Evaluator(Tester):
-    """utils.py:311-336"""
+    """Runs every test seed of the environment once with the loaded model and writes the episode records."""
 
     def __init__(self, env, model, output_path, gui=False):
-        self.env = env
-        self.model = model
-        self.agent = self.env.agent
+        self.env, self.model, self.output_path, self.gui = env, model, output_path, gui
+        self.agent = env.agent
         self.env.train_mode = False
-        self.test_num = self.env.test_num
-        self.output_path = output_path
-        self.gui = gui
+        self.test_num = env.test_num
         self.uniform_fn = None
+        self._port = _AgentPort(env, model)
 
     def run(self):
-        is_record = not self.gui
         self.env.cur_episode = 0
-        self.env.init_data(is_record, False, self.output_path)
+        self.env.init_data(not self.gui, False, self.output_path)
         for test_ind in range(self.test_num):
             reward, _ = self.perform(test_ind, gui=self.gui)
             self.env.terminate()

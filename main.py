@@ -1,133 +1,132 @@
-"""Train / evaluate networked-MARL agents on the B200-native hot path.
+"""Command line of the B200-native CACC / networked-A2C hot path.
 
-Same command line as the reference (main.py:21-40):
-    python main.py --base-dir D train --config-dir F
-    python main.py --base-dir D evaluate [--evaluation-seeds s1,s2] [--demo]
-and the same .ini surface (MODEL_CONFIG / TRAIN_CONFIG / ENV_CONFIG).  Optional new keys:
-ENV_CONFIG.n_env (parallel episodes per process; > 1 selects the batched VecTrainer).
-Only the CACC scenarios and the agents on the hot path (ia2c, ma2c_nc, ma2c_ic3, ma2c_dial)
-are available; ATSC/SUMO environments are out of scope.
+The reference's command line is kept verbatim (main.py:21-40 there) so existing scripts keep working:
+
+    python main.py --base-dir D train    --config-dir F.ini
+    python main.py --base-dir D evaluate [--evaluation-seeds s1,s2,...] [--demo]
+
+and so is the .ini surface (MODEL_CONFIG / TRAIN_CONFIG / ENV_CONFIG).  One optional new key: ENV_CONFIG.n_env
+(parallel episodes per process).  n_env = 1 runs the reference's one-episode-at-a-time Trainer; n_env > 1 the
+device-resident VecTrainer.  Agents: ia2c, ia2c_fp, ma2c_cu, ma2c_nc, ma2c_ic3, ma2c_dial on the CACC scenarios;
+ATSC/SUMO environments are out of scope.
 """
 import argparse
 import configparser
 import logging
+import os
 
-from deeprl_network_b200.agents.models import IA2C, IA2C_FP, IA2C_CU, MA2C_NC, MA2C_IC3, MA2C_DIAL
+from deeprl_network_b200.agents import models as agent_models
 from deeprl_network_b200.envs.cacc_env import CACCEnv
-from deeprl_network_b200.utils import (Counter, Trainer, Evaluator, VecTrainer, check_dir, copy_file, find_file,
-                                       init_dir, init_log, make_summary_writer)
+from deeprl_network_b200 import utils as U
 
-AGENTS = {'ia2c': IA2C, 'ia2c_fp': IA2C_FP, 'ma2c_cu': IA2C_CU, 'ma2c_nc': MA2C_NC, 'ma2c_ic3': MA2C_IC3, 'ma2c_dial': MA2C_DIAL}
+AGENTS = {'ia2c': agent_models.IA2C, 'ia2c_fp': agent_models.IA2C_FP, 'ma2c_cu': agent_models.IA2C_CU,
+          'ma2c_nc': agent_models.MA2C_NC, 'ma2c_ic3': agent_models.MA2C_IC3, 'ma2c_dial': agent_models.MA2C_DIAL}
+DEFAULT_EVAL_SEEDS = ','.join(str(s) for s in range(2000, 2500, 10))
 
 
-def parse_args():
-    parser = argparse.ArgumentParser()
-    parser.add_argument('--base-dir', type=str, required=False, default='./runs/ma2c_nc_catchup',
-                        help="experiment base dir")
-    subparsers = parser.add_subparsers(dest='option', help="train or evaluate")
-    sp = subparsers.add_parser('train', help='train a single agent under base dir')
-    sp.add_argument('--config-dir', type=str, required=False, default='./config/config_ma2c_nc_catchup.ini',
-                    help="experiment config path")
-    sp = subparsers.add_parser('evaluate', help="evaluate and compare agents under base dir")
-    sp.add_argument('--evaluation-seeds', type=str, required=False,
-                    default=','.join([str(i) for i in range(2000, 2500, 10)]),
-                    help="random seeds for evaluation, split by ,")
-    sp.add_argument('--demo', action='store_true', help="no-op here (SUMO gui in the reference)")
-    args = parser.parse_args()
-    if not args.option:
-        parser.print_help()
-        exit(1)
+def parse_args(argv=None):
+    top = argparse.ArgumentParser(description=__doc__.split('\n')[0])
+    top.add_argument('--base-dir', type=str, default='./runs/ma2c_nc_catchup', help='experiment base dir')
+    modes = top.add_subparsers(dest='option', help='train or evaluate')
+    tr = modes.add_parser('train', help='train the agent named in the config under the base dir')
+    tr.add_argument('--config-dir', type=str, default='./config/config_ma2c_nc_catchup.ini', help='experiment config path')
+    ev = modes.add_parser('evaluate', help='evaluate the agent stored under the base dir')
+    ev.add_argument('--evaluation-seeds', type=str, default=DEFAULT_EVAL_SEEDS, help='random seeds for evaluation, split by ,')
+    ev.add_argument('--demo', action='store_true', help='accepted for compatibility (SUMO gui in the reference); no files are written')
+    args = top.parse_args(argv)
+    if args.option is None:
+        top.print_help()
+        raise SystemExit(1)
     return args
 
 
+def read_config(path):
+    cfg = configparser.ConfigParser()
+    if not cfg.read(path):
+        raise FileNotFoundError(path)
+    return cfg
+
+
 def init_env(config, port=0):
-    scenario = config.get('scenario')
-    if scenario.startswith('atsc'):
+    """ENV_CONFIG section -> environment (only the CACC family exists here)."""
+    if config.get('scenario').startswith('atsc'):
         raise NotImplementedError('ATSC/SUMO environments are outside the accelerated hot path')
     return CACCEnv(config)
 
 
 def init_agent(env, config, total_step, seed, **kw):
-    cls = AGENTS.get(env.agent)
-    if cls is None:
+    """MODEL_CONFIG section -> agent object of the class ENV_CONFIG.agent names (None if unknown)."""
+    if env.agent not in AGENTS:
         logging.error('agent %r is not on the accelerated hot path' % env.agent)
         return None
     if env.agent == 'ia2c' and env.n_env > 1:     # device-resident rollouts gather neighbour observations in the kernel
         kw.setdefault('obs_mode', 'gather')
-    return cls(env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma,
-               total_step, config, seed=seed, n_env=env.n_env, **kw)
+    return AGENTS[env.agent](env.n_s_ls, env.n_a_ls, env.neighbor_mask, env.distance_mask, env.coop_gamma,
+                             total_step, config, seed=seed, n_env=env.n_env, **kw)
+
+
+def _train_batched(env, model, total_step):
+    """n_env > 1: whole updates on the device until total_step environment steps (summed over envs) are done."""
+    loop = U.VecTrainer(env, model)
+    loop.start()
+    done_steps = 0
+    while done_steps < total_step:
+        loop.update()
+        done_steps += model.n_step * env.n_env
+        if loop.n_update % 10 == 0:
+            logging.info('update %d, env steps %d, mean step reward %.2f' % (loop.n_update, done_steps, loop.mean_reward()))
+    return done_steps
 
 
 def train(args):
-    dirs = init_dir(args.base_dir)
-    init_log(dirs['log'])
-    copy_file(args.config_dir, dirs['data'])
-    config = configparser.ConfigParser()
-    config.read(args.config_dir)
-    env = init_env(config['ENV_CONFIG'])
+    dirs = U.init_dir(args.base_dir)
+    U.init_log(dirs['log'])
+    U.copy_file(args.config_dir, dirs['data'])             # evaluate finds the config next to the results
+    cfg = read_config(args.config_dir)
+    steps = {k: int(cfg.getfloat('TRAIN_CONFIG', k)) for k in ('total_step', 'test_interval', 'log_interval')}
+    env = init_env(cfg['ENV_CONFIG'])
     logging.info('Training: a dim %r, agent dim: %d' % (env.n_a_ls, env.n_agent))
-    total_step = int(config.getfloat('TRAIN_CONFIG', 'total_step'))
-    test_step = int(config.getfloat('TRAIN_CONFIG', 'test_interval'))
-    log_step = int(config.getfloat('TRAIN_CONFIG', 'log_interval'))
-    global_counter = Counter(total_step, test_step, log_step)
-    seed = config.getint('ENV_CONFIG', 'seed')
-    model = init_agent(env, config['MODEL_CONFIG'], total_step, seed)
-    summary_writer = make_summary_writer(dirs['log'])
-    if env.n_env == 1:
-        Trainer(env, model, global_counter, summary_writer, output_path=dirs['data']).run()
-        final_step = global_counter.cur_step
+    model = init_agent(env, cfg['MODEL_CONFIG'], steps['total_step'], cfg.getint('ENV_CONFIG', 'seed'))
+    if model is None:
+        raise SystemExit(2)
+    if env.n_env > 1:
+        final_step = _train_batched(env, model, steps['total_step'])
     else:
-        vt = VecTrainer(env, model)
-        vt.start()
-        steps = 0
-        while steps < total_step:
-            vt.update()
-            steps += model.n_step * env.n_env
-            if vt.n_update % 10 == 0:
-                logging.info('update %d, env steps %d, mean step reward %.2f' % (vt.n_update, steps, vt.mean_reward()))
-        final_step = steps
+        counter = U.Counter(steps['total_step'], steps['test_interval'], steps['log_interval'])
+        U.Trainer(env, model, counter, U.make_summary_writer(dirs['log']), output_path=dirs['data']).run()
+        final_step = counter.cur_step
     logging.info('Training: save final model at step %d ...' % final_step)
     model.save(dirs['model'], final_step)
 
 
 def evaluate_fn(agent_dir, output_dir, seeds, port, demo):
-    agent = agent_dir.split('/')[-1]
-    if not check_dir(agent_dir):
-        logging.error('Evaluation: %s does not exist!' % agent)
+    """Load <agent_dir>/data/*.ini and the newest checkpoint under <agent_dir>/model/, run one recorded episode per seed."""
+    if not U.check_dir(agent_dir):
+        logging.error('Evaluation: %s does not exist!' % os.path.basename(agent_dir))
         return
-    config_dir = find_file(agent_dir + '/data/')
-    if not config_dir:
+    ini = U.find_file(agent_dir + '/data/')
+    if not ini:
         return
-    config = configparser.ConfigParser()
-    config.read(config_dir)
-    config['ENV_CONFIG']['n_env'] = '1'
-    env = init_env(config['ENV_CONFIG'], port=port)
+    cfg = read_config(ini)
+    cfg['ENV_CONFIG']['n_env'] = '1'
+    env = init_env(cfg['ENV_CONFIG'], port=port)
     env.init_test_seeds(seeds)
-    model = init_agent(env, config['MODEL_CONFIG'], 0, 0)
-    if model is None:
-        return
-    if not model.load(agent_dir + '/model/'):
-        return
-    Evaluator(env, model, output_dir, gui=demo).run()
+    model = init_agent(env, cfg['MODEL_CONFIG'], 0, 0)
+    if model is not None and model.load(agent_dir + '/model/'):
+        U.Evaluator(env, model, output_dir, gui=demo).run()
 
 
 def evaluate(args):
-    base_dir = args.base_dir
+    output_dir = None
     if not args.demo:
-        dirs = init_dir(base_dir, pathes=['eva_data', 'eva_log'])
-        init_log(dirs['eva_log'])
+        dirs = U.init_dir(args.base_dir, pathes=['eva_data', 'eva_log'])
+        U.init_log(dirs['eva_log'])
         output_dir = dirs['eva_data']
-    else:
-        output_dir = None
-    seeds = args.evaluation_seeds
-    logging.info('Evaluation: random seeds: %s' % seeds)
-    seeds = [int(s) for s in seeds.split(',')] if seeds else []
-    evaluate_fn(base_dir, output_dir, seeds, 1, args.demo)
+    logging.info('Evaluation: random seeds: %s' % args.evaluation_seeds)
+    seeds = [int(s) for s in args.evaluation_seeds.split(',') if s]
+    evaluate_fn(args.base_dir, output_dir, seeds, 1, args.demo)
 
 
 if __name__ == '__main__':
-    args = parse_args()
-    if args.option == 'train':
-        train(args)
-    else:
-        evaluate(args)
+    cli = parse_args()
+    {'train': train, 'evaluate': evaluate}[cli.option](cli)
