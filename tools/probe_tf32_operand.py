@@ -1,0 +1,41 @@
+"""Hardware probe for DESIGN.md 6.2: does the TF32 tensor-core datapath ignore the 13 low mantissa bits of a
+shared-memory operand?  Runs the stand-alone 3xTF32 GEMM twice -- hi tile = masked values (what the product packs)
+and hi tile = raw fp32 values -- and reports whether the accumulators are bit-identical.  Run on a B200:
+    python tools/probe_tf32_operand.py"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deeprl_network_b200 import _lib as L  # noqa: E402
+
+
+def main():
+    lib = L.lib()
+    args = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p] * 3
+    lib.nmarl_tc_gemm_selftest.argtypes = args
+    lib.nmarl_tc_gemm_selftest_raw.argtypes = args
+    torch.manual_seed(0)
+    for (M, K, N) in [(256, 256, 256), (128, 64, 64), (512, 192, 256)]:
+        a = torch.randn(M, K, device='cuda') * torch.logspace(-3, 3, K, device='cuda')
+        w = torch.randn(K, N, device='cuda')
+        out = []
+        for fn in (lib.nmarl_tc_gemm_selftest, lib.nmarl_tc_gemm_selftest_raw):
+            c = torch.zeros(M, N, device='cuda')
+            scratch = torch.zeros(((K + 31) // 32) * 2 * N * 32, device='cuda')
+            err = torch.zeros(1, dtype=torch.int32, device='cuda')
+            L.check(fn(a.data_ptr(), w.data_ptr(), c.data_ptr(), M, K, N, scratch.data_ptr(), err.data_ptr(), L.stream()), 'selftest')
+            torch.cuda.synchronize()
+            assert int(err.item()) == 0
+            out.append(c)
+        ref = (a.double() @ w.double())
+        same = torch.equal(out[0], out[1])
+        print('M=%d K=%d N=%d: raw-operand GEMM %s the masked one; max rel err masked %.2e raw %.2e' % (
+            M, K, N, 'bit-identical to' if same else 'DIFFERS from',
+            float(((out[0] - ref).abs().max() / ref.abs().max())), float(((out[1] - ref).abs().max() / ref.abs().max()))))
+
+
+if __name__ == '__main__':
+    main()
