@@ -17,6 +17,7 @@ struct BwdK {
   float* dpT;                                                          // step t: [N][B/32][hi|lo][ndp][32] tiles (encoder pre-act grads)
   int state_fm;                                                        // c/dh/dc/dmsg tensors are feature-major
   int ndp;                                                             // rows of a dpT tile: 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C)
+  int raw_tiles;                                                       // experimental (NMARL_RAW_TILES): dzT/dpT hold one raw fp32 tile, no [hi|lo] pair
 };
 
 int nmarl_tc_launch_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st);
@@ -25,4 +26,5 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m);
 int nmarl_tc_ndp(const nmarl_model* m);
 // all GEMM weight gradients (gate + encoders) of the tensor-core path; activations are feature-major
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
-                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias);
+                           const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias,
+                           bool raw_tiles = false);

@@ -10,7 +10,9 @@
 namespace {
 using namespace tcrow;
 
-template <int VAR, bool FM>
+// RAW (experimental): the operand tiles for the weight-gradient GEMMs are stored once as raw fp32
+// instead of as a [hi | lo] pair; the weight-gradient kernel derives lo in shared memory.
+template <int VAR, bool FM, bool RAW>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid_constant__ nmarl_model m,
                                                                     const __grid_constant__ BwdK k) {
   extern __shared__ uint8_t smem_raw[];
@@ -141,13 +143,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       }
       st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);              // feature-major copy for the gate-bias column sums
       if (k.dzT != nullptr) {                 // dz^T tile for the tensor-core wgrad: K-major over rows, hi | lo
-        uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * 256 * 128);
+        uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)((RAW ? 1 : 2) * 256 * 128);
 #pragma unroll
         for (int j = 0; j < EW; ++j) {
           const uint32_t off = tc::sw128_offset((uint32_t)(g * NH + e0 + j), (uint32_t)lane);
-          const float hi = __uint_as_float(__float_as_uint(dz[j]) & 0xFFFFE000u);
-          __stcs(reinterpret_cast<float*>(tile + off), hi);                       // read once, by the wgrad kernel
-          __stcs(reinterpret_cast<float*>(tile + 256 * 128 + off), dz[j] - hi);
+          if constexpr (RAW) {
+            __stcs(reinterpret_cast<float*>(tile + off), dz[j]);
+          } else {
+            const float hi = __uint_as_float(__float_as_uint(dz[j]) & 0xFFFFE000u);
+            __stcs(reinterpret_cast<float*>(tile + off), hi);                       // read once, by the wgrad kernel
+            __stcs(reinterpret_cast<float*>(tile + 256 * 128 + off), dz[j] - hi);
+          }
         }
       }
       produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
@@ -160,15 +166,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < EW; ++j) dpm[j] = 0.f;
     uint8_t* dptile = (k.dpT != nullptr)
-        ? reinterpret_cast<uint8_t*>(k.dpT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)(2 * k.ndp * 128) : nullptr;
+        ? reinterpret_cast<uint8_t*>(k.dpT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)((RAW ? 1 : 2) * k.ndp * 128) : nullptr;
     auto put_dp = [&](int n0, const float (&vals)[EW]) {        // encoder pre-activation grads as K-major tiles
       if (dptile == nullptr) return;
 #pragma unroll
       for (int j = 0; j < EW; ++j) {
         const uint32_t off = tc::sw128_offset((uint32_t)(n0 + j), (uint32_t)lane);
-        const float hi = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
-        __stcs(reinterpret_cast<float*>(dptile + off), hi);
-        __stcs(reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off), vals[j] - hi);
+        if constexpr (RAW) {
+          __stcs(reinterpret_cast<float*>(dptile + off), vals[j]);
+        } else {
+          const float hi = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
+          __stcs(reinterpret_cast<float*>(dptile + off), hi);
+          __stcs(reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off), vals[j] - hi);
+        }
       }
     };
 #pragma unroll
@@ -246,9 +256,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
   if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }
 }
 
-template <int VAR, bool FM>
+template <int VAR, bool FM, bool RAW>
 int launch_tc_bwd_fm(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
-  auto kern = tc_cell_bwd_kernel<VAR, FM>;
+  auto kern = tc_cell_bwd_kernel<VAR, FM, RAW>;
   static bool configured = false;
   if (!configured) {
     NMARL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -262,7 +272,8 @@ int launch_tc_bwd_fm(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
 
 template <int VAR>
 int launch_tc_bwd(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
-  return k.state_fm ? launch_tc_bwd_fm<VAR, true>(m, k, st) : launch_tc_bwd_fm<VAR, false>(m, k, st);
+  if (k.raw_tiles) return k.state_fm ? launch_tc_bwd_fm<VAR, true, true>(m, k, st) : launch_tc_bwd_fm<VAR, false, true>(m, k, st);
+  return k.state_fm ? launch_tc_bwd_fm<VAR, true, false>(m, k, st) : launch_tc_bwd_fm<VAR, false, false>(m, k, st);
 }
 
 }  // namespace

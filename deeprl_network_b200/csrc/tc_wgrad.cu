@@ -54,6 +54,11 @@ __device__ __forceinline__ JobDesc job_desc(const nmarl_model& m, const TcWgK& k
   return d;
 }
 
+// RAW (experimental): the D^T tiles hold raw fp32 once.  The producer copies one tile per k-block; it
+// doubles as the hi operand (the TF32 datapath drops the 13 low mantissa bits -- tools/probe_tf32_operand.py); the
+// row threads derive lo = x - trunc(x) into the second half of the stage and signal lo_full; the issuer runs the two
+// passes that need only the raw tile first and a_hi * b_lo after that barrier.
+template <bool RAW>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ nmarl_model m,
                                                                  const __grid_constant__ TcWgK k) {
   extern __shared__ uint8_t smem_raw[];
@@ -62,7 +67,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
   uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
   uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* lo_full = acc_full + 1;                                    // RAW only: S_STAGES barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1 + (RAW ? S_STAGES : 0));
 
   const int sp = blockIdx.x, jslot = blockIdx.y, i = blockIdx.z;
   const int kind = k.jobs[jslot];
@@ -81,6 +87,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
+    if constexpr (RAW)
+      for (int s = 0; s < S_STAGES; ++s) tc::mbar_init(&lo_full[s], ROW_THREADS);
     tc::fence_barrier_init();
   }
   if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
@@ -89,6 +97,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tile_bytes = (uint32_t)d.N * 128u;                   // hi (or lo) part staged per k-block
+  // byte offset of the D^T tile of (t, 32-env block rb): [hi | lo] pairs, or single raw tiles packed inside each
+  // time step's (unchanged) [hi | lo]-sized slab
+  auto bt_tile = [&](int t, int rb) -> const uint8_t* {
+    const size_t pair = (size_t)(2 * d.tile_rows * 128);
+    const size_t off = RAW ? (size_t)t * N_agents * bpt * pair + ((size_t)i * bpt + rb) * (pair / 2)
+                           : (((size_t)t * N_agents + i) * bpt + rb) * pair;
+    return reinterpret_cast<const uint8_t*>(d.BT) + off;
+  };
 
   if (warp < ROW_THREADS / 32) {
     RowCtx c;
@@ -115,6 +131,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         for (int j = 0; j < W; ++j) x[j] = one ? 1.0f : 0.0f;
       }
       produce_in(c, x);
+      if constexpr (RAW) {                                              // lo half of this k-block's B stage
+        const int st = q % S_STAGES;
+        tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 41);
+        const float4* raw = reinterpret_cast<const float4*>(bst + st * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(bst + st * STAGE_BYTES + tile_bytes);
+        for (uint32_t e = (uint32_t)tid; e < tile_bytes / 16; e += ROW_THREADS) {
+          const float4 v = raw[e];
+          float4 l;
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          lo[e] = l;
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&lo_full[st]);
+      }
     }
     // tcgen05.ld is warp-collective (.sync.aligned): the condition must be warp-uniform; stores are per lane
     const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;
@@ -141,10 +174,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const int kb = kb0 + q, st = q % S_STAGES;
         const int t = kb / bpt, rb = kb - t * bpt;
         tc::mbar_wait(&b_empty[st], ((q / S_STAGES) & 1) ^ 1, k.err, 21);
-        tc::mbar_arrive_expect_tx(&b_full[st], 2 * tile_bytes);
-        const uint8_t* tile = reinterpret_cast<const uint8_t*>(d.BT) + (((size_t)t * N_agents + i) * bpt + rb) * (size_t)(2 * d.tile_rows * 128);
-        tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
-        tc::bulk_g2s(bst + st * STAGE_BYTES + tile_bytes, tile + (size_t)(d.tile_rows + d.n_row0) * 128, tile_bytes, &b_full[st]);
+        const uint8_t* tile = bt_tile(t, rb);
+        if constexpr (RAW) {
+          tc::mbar_arrive_expect_tx(&b_full[st], tile_bytes);
+          tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
+        } else {
+          tc::mbar_arrive_expect_tx(&b_full[st], 2 * tile_bytes);
+          tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
+          tc::bulk_g2s(bst + st * STAGE_BYTES + tile_bytes, tile + (size_t)(d.tile_rows + d.n_row0) * 128, tile_bytes, &b_full[st]);
+        }
       }
     }
   } else {
@@ -156,12 +194,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         tc::mbar_wait(&a_full[slot], (q >> 1) & 1, k.err, 32);
         tc::fence_after_sync();
         const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile_bytes);
+        if constexpr (RAW) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
-          tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_hi + 2 * ks, idesc, (q == 0 && ks == 0) ? 0u : 1u);
-          tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_lo + 2 * ks, idesc, 1u);
-          tc::mma_tf32_ts(tmem + ACC_COL, a_lo, d_hi + 2 * ks, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) {                              // passes that need only the raw tile
+            const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
+            tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_hi + 2 * ks, idesc, (q == 0 && ks == 0) ? 0u : 1u);
+            tc::mma_tf32_ts(tmem + ACC_COL, a_lo, d_hi + 2 * ks, idesc, 1u);
+          }
+          tc::mbar_wait(&lo_full[st], (q / S_STAGES) & 1, k.err, 33);
+          tc::fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc::mma_tf32_ts(tmem + ACC_COL, tmem + A_COL + slot * 64 + ks * 8, d_lo + 2 * ks, idesc, 1u);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = tmem + A_COL + slot * 64 + ks * 8, a_lo = a_hi + 32;
+            tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_hi + 2 * ks, idesc, (q == 0 && ks == 0) ? 0u : 1u);
+            tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_lo + 2 * ks, idesc, 1u);
+            tc::mma_tf32_ts(tmem + ACC_COL, a_lo, d_hi + 2 * ks, idesc, 1u);
+          }
         }
         tc::mma_commit(&a_empty[slot]);
         tc::mma_commit(&b_empty[st]);
@@ -254,7 +306,7 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
 
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
                            const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st,
-                           cudaStream_t st_bias) {
+                           cudaStream_t st_bias, bool raw_tiles) {
   TcWgK k{};
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
@@ -263,12 +315,14 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
   for (int j = 0; j < k.n_jobs; ++j) { k.ws_off[j] = off; off += (long long)k.splits * m->n_agent * 128 * job_N(m, k.jobs[j]); }
   static bool configured = false;
   if (!configured) {
-    NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
   dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B, T, grads);   // independent of the GEMM jobs
   NMARL_LAUNCH_CHECK();
-  tc_wgrad_kernel<<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
+  if (raw_tiles) tc_wgrad_kernel<true><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
+  else tc_wgrad_kernel<false><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   NMARL_DBG_SYNC(st, "tc_wgrad_kernel");
   tc_wgrad_reduce_kernel<<<dim3(64, k.n_jobs, m->n_agent), 256, 0, st>>>(*m, k, grads);

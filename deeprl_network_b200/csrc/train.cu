@@ -904,6 +904,8 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   }
   NMARL_CUDA(cudaEventRecord(ev_join, side));
   // 2. reverse time
+  static int raw_tiles = -1;           // experimental single-copy operand tiles; off unless NMARL_RAW_TILES is set
+  if (raw_tiles < 0) raw_tiles = (getenv("NMARL_RAW_TILES") != nullptr) ? 1 : 0;
   for (int t = T - 1; t >= 0; --t) {
     BwdK k{};
     k.B = B; k.t = t; k.has_next = (t < T - 1);
@@ -925,6 +927,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     k.sv_dz = a->sv_dz + (size_t)t * nb * NG;
     k.sv_dpre = a->sv_dpre + (size_t)t * nb * 192;
     k.wpack = a->wpack; k.tc_err = a->tc_err; k.state_fm = a->state_fm;
+    k.raw_tiles = raw_tiles;
     const bool use_tc = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
     k.dzT = (use_tc && a->sv_dzT) ? a->sv_dzT + (size_t)t * N * (B / 32) * (2 * 256 * 32) : nullptr;
     k.ndp = nmarl_tc_ndp(m);
@@ -958,7 +961,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     // the gate-bias column sums only read sv_dz: second fork, beside the GEMM jobs
     NMARL_CUDA(cudaEventRecord(ev_fork, st));
     NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side)) return 1;
+    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side, raw_tiles != 0)) return 1;
     NMARL_CUDA(cudaEventRecord(ev_join, side));
     NMARL_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     NMARL_DBG_SYNC(st, "tc_wgrads");
