@@ -68,12 +68,13 @@ class BwdArgs(C.Structure):
                 ('dh_rec', C.c_void_p), ('dc_rec', C.c_void_p), ('dmsg', C.c_void_p),
                 ('wt', C.c_void_p), ('ws', C.c_void_p), ('ws_floats', C.c_int64),
                 ('loss_part', C.c_void_p), ('grads', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
-                ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p), ('state_fm', C.c_int32)]
+                ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p), ('state_fm', C.c_int32),
+                ('ctx', C.c_void_p), ('raw_tiles', C.c_int32), ('ev_step', C.c_void_p), ('ev_wgrad', C.c_void_p)]
 
 
 _lib = None
 
-EXPORTS = ['nmarl_last_error', 'nmarl_version', 'nmarl_sizeof_model', 'nmarl_sizeof_agent', 'nmarl_sizeof_cacc_cfg',
+EXPORTS = ['nmarl_last_error', 'nmarl_version', 'nmarl_create', 'nmarl_destroy', 'nmarl_sizeof_bwd_args', 'nmarl_sizeof_fwd_args', 'nmarl_sizeof_model', 'nmarl_sizeof_agent', 'nmarl_sizeof_cacc_cfg',
            'nmarl_cacc_reset', 'nmarl_cacc_step', 'nmarl_pack_weights', 'nmarl_policy_step_p', 'nmarl_policy_step_v', 'nmarl_dial_msg',
            'nmarl_rng_advance', 'nmarl_nstep_return_adv', 'nmarl_loss_tiles', 'nmarl_ws_floats',
            'nmarl_a2c_backward', 'nmarl_a2c_train_forward', 'nmarl_a2c_bptt', 'nmarl_a2c_train_heads',
@@ -92,6 +93,8 @@ def lib():
     L.nmarl_last_error.restype = C.c_char_p
     L.nmarl_ws_floats.restype = C.c_int64
     P, I, D, F, U64 = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_uint64
+    L.nmarl_create.argtypes = [C.POINTER(C.c_void_p)]
+    L.nmarl_destroy.argtypes = [P]
     L.nmarl_cacc_reset.argtypes = [C.POINTER(CaccCfg), I, P, P, U64, P, P, P, P, P, P, P, P, I, P, I, P]
     L.nmarl_cacc_step.argtypes = [C.POINTER(CaccCfg), I, I, P, P, P, P, P, P, P, P, I, P, P, P, P]
     L.nmarl_policy_step_p.argtypes = [C.POINTER(Model), C.POINTER(FwdArgs), P]
@@ -109,6 +112,8 @@ def lib():
     assert L.nmarl_sizeof_model() == C.sizeof(Model), 'nmarl_model layout mismatch'
     assert L.nmarl_sizeof_agent() == C.sizeof(Agent), 'nmarl_agent layout mismatch'
     assert L.nmarl_sizeof_cacc_cfg() == C.sizeof(CaccCfg), 'nmarl_cacc_cfg layout mismatch'
+    assert L.nmarl_sizeof_bwd_args() == C.sizeof(BwdArgs), 'nmarl_bwd_args layout mismatch'
+    assert L.nmarl_sizeof_fwd_args() == C.sizeof(FwdArgs), 'nmarl_fwd_args layout mismatch'
     _lib = L
     return L
 

@@ -98,7 +98,21 @@ class PolicyEngine:
         self.kernel_events = None          # bench.py: list collecting (start, end) CUDA events around each rollout p-call
         self.T_cur = T
         self.launches = 0
+        # single-copy operand tiles for the weight-gradient GEMMs (nmarl_bwd_args.raw_tiles)
+        self.raw_tiles = self.use_tc and os.environ.get('NMARL_RAW_TILES', '0') == '1'
+        self.bwd_events = None             # bench.py: (step events [2T], wgrad events [2]) recorded inside nmarl_a2c_bptt
+        self._ctx = C.c_void_p()
+        L.check(L.lib().nmarl_create(C.byref(self._ctx)), 'nmarl_create')
         self.repack()
+
+    def __del__(self):
+        ctx = getattr(self, '_ctx', None)
+        if ctx is not None and ctx.value:
+            try:
+                L.lib().nmarl_destroy(ctx)
+            except Exception:
+                pass
+            self._ctx = None
 
     # ---- state ----------------------------------------------------------------------------------
     def reset_states(self, mask=None):
@@ -352,6 +366,13 @@ class PolicyEngine:
         a.wpack, a.tc_err = L.ptr(self.wpack), L.ptr(self.tc_err)
         a.sv_dzT, a.sv_dpT = L.ptr(self.sv_dzT), L.ptr(self.sv_dpT)
         a.state_fm = int(self.state_fm)
+        a.ctx, a.raw_tiles = self._ctx, int(self.raw_tiles)
+        if self.bwd_events is not None:
+            step_ev, wg_ev = self.bwd_events
+            self._ev_arrays = ((C.c_void_p * len(step_ev))(*[ev.cuda_event for ev in step_ev]),
+                               (C.c_void_p * 2)(*[ev.cuda_event for ev in wg_ev]))
+            a.ev_step = C.cast(self._ev_arrays[0], C.c_void_p)
+            a.ev_wgrad = C.cast(self._ev_arrays[1], C.c_void_p)
         return a
 
     def backward(self):

@@ -3,6 +3,13 @@
 #pragma once
 #include "common.cuh"
 
+// the opaque context of the C ABI: helper stream + events for forked side work (created on the current device)
+struct nmarl_ctx {
+  cudaStream_t side;
+  cudaEvent_t fork, join;
+  int device;
+};
+
 struct BwdK {
   int B, t, has_next;
   const float* params; const float* wt;
@@ -27,4 +34,4 @@ int nmarl_tc_ndp(const nmarl_model* m);
 // all GEMM weight gradients (gate + encoders) of the tensor-core path; activations are feature-major
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
                            const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias,
-                           bool raw_tiles = false);
+                           bool raw_tiles = false, void** ev_wgrad = nullptr);

@@ -2,10 +2,8 @@
 // Compiled with --fmad=false: the reference is NumPy float64 without FMA contraction, and the
 // kernels below keep its operation order so h, v, u and the rewards are bit-identical.
 //
-// One thread owns one environment and sweeps its N vehicles in ascending order (the vehicle
-// chain is a serial dependence: headway i needs the old AND new speed of vehicle i-1).  All
-// arrays are [agent][env], so a warp's loads/stores are coalesced over envs.  The kernel is
-// latency-bound and tiny next to the policy kernels (N*45 B of HBM traffic per env-step).
+// Step kernel: one thread per (env, agent) -- see cacc_step_kernel.  Reset kernel: one thread per env (off the
+// critical path).  All arrays are [agent][env], so a warp's loads/stores are coalesced over envs.
 //
 // Restates envs/cacc_env.py: step :191-242, reward :40-52, observation :54-65,
 // OVM :360-385, reset :166-189 / :285-318.
@@ -84,87 +82,125 @@ __global__ void cacc_reset_kernel(const EnvK k, const double* __restrict__ u01, 
   }
 }
 
+// One thread per (env, agent): blockDim = (32 envs, N agents), so a warp is one agent over 32 consecutive envs
+// (coalesced [agent][env] accesses) and the serial vehicle chain of the reference disappears: vehicle i's update
+// needs its predecessor's OLD and NEW speed, and the predecessor's new speed depends only on the predecessor's own
+// old state (and on ITS predecessor's old speed) -- each thread recomputes it with the very same operations, so
+// every number is bit-identical to the sequential sweep.  Reads of the old state, __syncthreads, then writes.
+// The per-env reductions (collision = min headway, global reward = np.sum over agents) run in shared memory in the
+// reference's order (sequential / 8 strided accumulators + pairwise tree, exactly what np.sum does).
+struct VehStep { double vn, uc; };
+__device__ __forceinline__ VehStep veh_update(const nmarl_cacc_cfg& c, int a, double h, double v, double lead) {
+  const double al = (a & 1) ? 0.5 : 0.0;          // a_map = [(0,0),(.5,0),(0,.5),(.5,.5)]  (:275)
+  const double be = (a & 2) ? 0.5 : 0.0;
+  const double u = al * (ovm_vh(c, h) - v) + be * (lead - v);
+  double vn = v + clipd(u, c.u_min, c.u_max) * c.dt;
+  vn = clipd(vn, 0.0, c.v_max);
+  VehStep r;
+  r.vn = vn;
+  r.uc = (vn - v) / c.dt;
+  return r;
+}
+
 __global__ void cacc_step_kernel(const EnvK k, int train_mode, const int32_t* __restrict__ action, double* hs,
                                  double* vs, double* us, int32_t* t, int32_t* collision,
                                  const double* __restrict__ v_init, float* obs, int obs_stride, double* reward,
                                  double* greward, float* done) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const int B = k.B;
-  if (b >= B) return;
+  extern __shared__ double sm_env[];                 // [2][N][32]: per-agent reward, new headway
   const nmarl_cacc_cfg& c = k.c;
-  const int N = c.n_agent, L = c.platoon_len;
-  const int tcur = t[b];
-  int col = collision[b];
-  double gsum;
-  if (col) {                       // frozen after a collision: -G for every agent (:193-194)
-    for (int i = 0; i < N; ++i)
-      if (!c.global_reward) reward[(size_t)i * B + b] = -c.G;
-    gsum = -c.G * (double)N;       // sum of N equal values is exact in any order
-  } else {
-    double v_prev_old = 0.0, v_prev_new = 0.0, hmin = 1e300;
-    for (int i = 0; i < N; ++i) {
-      const int pos = i % L;
-      const size_t o = (size_t)i * B + b;
-      const double v = vs[o], h = hs[o];
+  const int N = c.n_agent, L = c.platoon_len, B = k.B;
+  const int e = threadIdx.x, i = threadIdx.y;
+  const int b = blockIdx.x * 32 + e;
+  const bool live = b < B;
+  double* s_r = sm_env;
+  double* s_h = sm_env + N * 32;
+  __shared__ int s_col[32];
+  const int pos = i % L;
+  const size_t o = (size_t)i * B + b;
+  int tcur = 0, col = 0;
+  double h = 0.0, v = 0.0, uo = 0.0, hn = 0.0, vn = 0.0, un = 0.0, lead_new = 0.0, vi0 = 0.0;
+  if (live) {
+    tcur = t[b]; col = collision[b];
+    h = hs[o]; v = vs[o]; uo = us[o];
+    vi0 = v_init[(size_t)(i / L) * B + b];
+    hn = h; vn = v; un = uo;
+    if (!col) {
       double lead, lead_next;
-      if (pos) { lead = v_prev_old; lead_next = v_prev_new; }
-      else {
-        const double vi = v_init[(size_t)(i / L) * B + b];
-        lead = leader_speed(c, vi, tcur);
-        lead_next = leader_speed(c, vi, tcur + 1);
+      if (pos) {
+        // predecessor's old state and ITS leader's old speed -> predecessor's new speed, recomputed locally
+        const double vp = vs[o - B], hp = hs[o - B];
+        const double lead_p = (pos > 1) ? vs[o - 2 * (size_t)B] : leader_speed(c, vi0, tcur);
+        lead = vp;
+        lead_next = veh_update(c, action[o - B], hp, vp, lead_p).vn;
+      } else {
+        lead = leader_speed(c, vi0, tcur);
+        lead_next = leader_speed(c, vi0, tcur + 1);
       }
-      const int a = action[o];
-      const double al = (a & 1) ? 0.5 : 0.0;          // a_map = [(0,0),(.5,0),(0,.5),(.5,.5)]  (:275)
-      const double be = (a & 2) ? 0.5 : 0.0;
-      const double u = al * (ovm_vh(c, h) - v) + be * (lead - v);
-      double vn = v + clipd(u, c.u_min, c.u_max) * c.dt;
-      vn = clipd(vn, 0.0, c.v_max);
-      const double uc = (vn - v) / c.dt;
-      const double hn = h + 0.5 * c.dt * (lead + lead_next - v - vn);
-      hs[o] = hn; vs[o] = vn; us[o] = uc;
-      v_prev_old = v; v_prev_new = vn;
-      hmin = fmin(hmin, hn);
+      const VehStep s = veh_update(c, action[o], h, v, lead);
+      vn = s.vn; un = s.uc;
+      hn = h + 0.5 * c.dt * (lead + lead_next - v - vn);
+      lead_new = lead_next;                          // leader's speed as the NEW observation sees it (pos > 0)
+      double r = -((hn - c.h_star) * (hn - c.h_star));
+      r = r + (-c.rew_a * ((vn - c.v_star) * (vn - c.v_star)));
+      r = r + (-c.rew_b * (un * un));
+      if (train_mode) {
+        const double m = fmin(hn - 10.0, 0.0);
+        r = r + (-5.0 * (m * m));
+      } else {
+        r = r + 0.0;
+      }
+      s_r[i * 32 + e] = r;
+      s_h[i * 32 + e] = hn;
+    } else if (pos) {
+      lead_new = vs[o - B];                          // frozen after a collision: the state does not move
     }
-    if (hmin < c.h_min) {          // collision latch (:42-44)
-      col = 1;
-      collision[b] = 1;
-      for (int i = 0; i < N; ++i)
-        if (!c.global_reward) reward[(size_t)i * B + b] = -c.G;
-      gsum = -c.G * (double)N;
+  }
+  __syncthreads();                                   // every old value has been read
+  if (live && !col) { hs[o] = hn; vs[o] = vn; us[o] = un; }
+  if (live && i == 0) {
+    double gsum;
+    int cnew = col;
+    if (!col) {
+      double hmin = 1e300;
+      for (int j = 0; j < N; ++j) hmin = fmin(hmin, s_h[j * 32 + e]);
+      if (hmin < c.h_min) { cnew = 1; collision[b] = 1; }       // collision latch (:42-44)
+    }
+    if (cnew) {
+      gsum = -c.G * (double)N;                       // sum of N equal values is exact in any order
     } else {
       // np.sum order: sequential for N < 8, otherwise 8 strided accumulators + pairwise tree + tail
       double r8[8];
       double tail = 0.0;
       const int nblk = N - (N % 8);
-      for (int i = 0; i < N; ++i) {
-        const size_t o = (size_t)i * B + b;
-        const double h = hs[o], v = vs[o], u = us[o];
-        double r = -((h - c.h_star) * (h - c.h_star));
-        r = r + (-c.rew_a * ((v - c.v_star) * (v - c.v_star)));
-        r = r + (-c.rew_b * (u * u));
-        if (train_mode) {
-          const double m = fmin(h - 10.0, 0.0);
-          r = r + (-5.0 * (m * m));
-        } else {
-          r = r + 0.0;
-        }
-        if (!c.global_reward) reward[o] = r;
+      for (int j = 0; j < N; ++j) {
+        const double r = s_r[j * 32 + e];
         if (N < 8) tail += r;
-        else if (i < 8) r8[i] = r;
-        else if (i < nblk) r8[i & 7] += r;
-        else { if (i == nblk) tail = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7])); tail += r; }
+        else if (j < 8) r8[j] = r;
+        else if (j < nblk) r8[j & 7] += r;
+        else { if (j == nblk) tail = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7])); tail += r; }
       }
       if (N >= 8 && N == nblk) tail = ((r8[0] + r8[1]) + (r8[2] + r8[3])) + ((r8[4] + r8[5]) + (r8[6] + r8[7]));
       gsum = tail;
     }
+    s_col[e] = cnew;
+    const int tn = tcur + 1;
+    t[b] = tn;
+    greward[b] = gsum;
+    if (c.global_reward) reward[b] = gsum;
+    const bool d = (cnew && (tn % c.batch_size == 0)) || (tn == c.T);
+    done[b] = d ? 1.0f : 0.0f;
   }
-  const int tn = tcur + 1;
-  t[b] = tn;
-  greward[b] = gsum;
-  if (c.global_reward) reward[b] = gsum;
-  const bool d = (col && (tn % c.batch_size == 0)) || (tn == c.T);
-  done[b] = d ? 1.0f : 0.0f;
-  write_obs(c, B, b, tn, hs, vs, us, v_init, obs, obs_stride);
+  __syncthreads();
+  if (!live) return;
+  if (!c.global_reward) reward[o] = s_col[e] ? -c.G : s_r[i * 32 + e];     // frozen / new collision: -G (:193-194)
+  // observation from the NEW state and the NEW time (:54-65)
+  const double lead = pos ? lead_new : leader_speed(c, vi0, tcur + 1);
+  float* ob = obs + o * obs_stride;
+  ob[0] = (float)((vn - c.v_star) / c.v_star);
+  ob[1] = (float)clipd((lead - vn) / 5.0, -2.0, 2.0);
+  ob[2] = (float)clipd((ovm_vh(c, hn) - vn) / 5.0, -2.0, 2.0);
+  ob[3] = (float)((hn + (lead - vn) * c.dt - c.h_star) / c.h_star);
+  ob[4] = (float)(un / c.u_max);
 }
 
 }  // namespace
@@ -188,10 +224,12 @@ extern "C" int nmarl_cacc_step(const nmarl_cacc_cfg* cfg, int B, int train_mode,
                                int obs_stride, double* reward, double* greward, float* done, void* stream) {
   NMARL_CHECK(cfg && B > 0 && action, "cacc_step: bad arguments");
   NMARL_CHECK(cfg->platoon_len > 0 && cfg->n_agent % cfg->platoon_len == 0, "cacc_step: n_agent %% platoon_len != 0");
+  NMARL_CHECK(cfg->n_agent <= 32, "cacc_step: n_agent > 32");
   EnvK k{*cfg, B};
-  const int nt = 64;
-  cacc_step_kernel<<<(B + nt - 1) / nt, nt, 0, (cudaStream_t)stream>>>(k, train_mode, action, hs, vs, us, t, collision,
-                                                                        v_init, obs, obs_stride, reward, greward, done);
+  const dim3 blk(32, cfg->n_agent);
+  const size_t smem = (size_t)2 * cfg->n_agent * 32 * sizeof(double);
+  cacc_step_kernel<<<(B + 31) / 32, blk, smem, (cudaStream_t)stream>>>(k, train_mode, action, hs, vs, us, t, collision,
+                                                                     v_init, obs, obs_stride, reward, greward, done);
   NMARL_LAUNCH_CHECK();
   return 0;
 }

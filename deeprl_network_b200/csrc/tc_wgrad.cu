@@ -306,7 +306,7 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
 
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
                            const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st,
-                           cudaStream_t st_bias, bool raw_tiles) {
+                           cudaStream_t st_bias, bool raw_tiles, void** ev_wgrad) {
   TcWgK k{};
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
@@ -321,9 +321,11 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
   }
   dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B, T, grads);   // independent of the GEMM jobs
   NMARL_LAUNCH_CHECK();
+  if (ev_wgrad) NMARL_CUDA(cudaEventRecord((cudaEvent_t)ev_wgrad[0], st));
   if (raw_tiles) tc_wgrad_kernel<true><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   else tc_wgrad_kernel<false><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
+  if (ev_wgrad) NMARL_CUDA(cudaEventRecord((cudaEvent_t)ev_wgrad[1], st));
   NMARL_DBG_SYNC(st, "tc_wgrad_kernel");
   tc_wgrad_reduce_kernel<<<dim3(64, k.n_jobs, m->n_agent), 256, 0, st>>>(*m, k, grads);
   NMARL_LAUNCH_CHECK();

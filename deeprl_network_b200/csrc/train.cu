@@ -874,21 +874,10 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   // 1b. policy/value head weight gradients need only sv_dlv and h_seq: they run on a forked stream
   //     beside the BPTT chain (whose 256-CTA launches leave SMs idle in their second wave) and join
   //     before the weight-gradient phase, which shares the workspace.
-  //     The helper stream and its two events are the library's only process-level state: created lazily,
-  //     once per device, by the first (un-captured) call; one host thread per device is assumed.
-  struct Fork { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-  static Fork forks[64];
-  int dev = 0;
-  NMARL_CUDA(cudaGetDevice(&dev));
-  NMARL_CHECK(dev >= 0 && dev < 64, "a2c_bptt: device ordinal %d out of range", dev);
-  Fork& fk = forks[dev];
-  if (!fk.side) {
-    NMARL_CUDA(cudaStreamCreateWithFlags(&fk.side, cudaStreamNonBlocking));
-    NMARL_CUDA(cudaEventCreateWithFlags(&fk.fork, cudaEventDisableTiming));
-    NMARL_CUDA(cudaEventCreateWithFlags(&fk.join, cudaEventDisableTiming));
-  }
-  cudaStream_t side = fk.side;
-  cudaEvent_t ev_fork = fk.fork, ev_join = fk.join;
+  //     The helper stream and its two events live in the caller's nmarl_ctx.
+  NMARL_CHECK(a->ctx != nullptr, "a2c_bptt: nmarl_bwd_args.ctx is NULL (nmarl_create)");
+  cudaStream_t side = a->ctx->side;
+  cudaEvent_t ev_fork = a->ctx->fork, ev_join = a->ctx->join;
   NMARL_CUDA(cudaEventRecord(ev_fork, st));
   NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   {
@@ -904,8 +893,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   }
   NMARL_CUDA(cudaEventRecord(ev_join, side));
   // 2. reverse time
-  static int raw_tiles = -1;           // experimental single-copy operand tiles; off unless NMARL_RAW_TILES is set
-  if (raw_tiles < 0) raw_tiles = (getenv("NMARL_RAW_TILES") != nullptr) ? 1 : 0;
+  const int raw_tiles = a->raw_tiles ? 1 : 0;      // single-copy operand tiles
   for (int t = T - 1; t >= 0; --t) {
     BwdK k{};
     k.B = B; k.t = t; k.has_next = (t < T - 1);
@@ -933,6 +921,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     k.ndp = nmarl_tc_ndp(m);
     k.dpT = (use_tc && a->sv_dpT) ? a->sv_dpT + (size_t)t * N * (B / 32) * (2 * k.ndp * 32) : nullptr;
     int rc = 0;
+    if (a->ev_step) NMARL_CUDA(cudaEventRecord((cudaEvent_t)a->ev_step[2 * t], st));
     if (use_tc) rc = nmarl_tc_launch_bwd(m, k, st);
     else
     switch (m->variant) {
@@ -942,6 +931,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
       case NMARL_DIAL: rc = launch_bwd<NMARL_DIAL>(m, k, st); break;
     }
     if (rc) return rc;
+    if (a->ev_step) NMARL_CUDA(cudaEventRecord((cudaEvent_t)a->ev_step[2 * t + 1], st));
     NMARL_DBG_SYNC(st, "cell_bwd");
     if (m->variant == NMARL_DIAL) {
       dim3 grid((B + 63) / 64, N);
@@ -961,7 +951,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     // the gate-bias column sums only read sv_dz: second fork, beside the GEMM jobs
     NMARL_CUDA(cudaEventRecord(ev_fork, st));
     NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side, raw_tiles != 0)) return 1;
+    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side, raw_tiles != 0, a->ev_wgrad)) return 1;
     NMARL_CUDA(cudaEventRecord(ev_join, side));
     NMARL_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     NMARL_DBG_SYNC(st, "tc_wgrads");

@@ -6,10 +6,13 @@
  * replaces (paths relative to the reference checkout).
  *
  * Conventions: extern "C"; every function returns 0 on success, non-zero on error
- * (message via nmarl_last_error()); never throws; never allocates device memory and keeps no
- * global state -- the caller owns every buffer and passes raw device pointers plus an explicit
- * stream (cudaStream_t passed as void*).  All launches are asynchronous on that stream and are
- * CUDA-graph capturable.  Device code is sm_100a only.
+ * (message via nmarl_last_error(), thread-local); never throws; never allocates device memory and
+ * keeps no global state -- the caller owns every buffer and passes raw device pointers plus an
+ * explicit stream (cudaStream_t passed as void*).  The only library-owned resources are the ones
+ * inside an opaque `nmarl_ctx`: one helper stream + two events used to fork side work beside the
+ * BPTT chain, created by nmarl_create and freed by nmarl_destroy; entry points that fork take
+ * the ctx through their argument block.  Re-entrant per ctx, not thread-safe per ctx.  All launches
+ * are asynchronous on the given stream and are CUDA-graph capturable.  Device code is sm_100a only.
  *
  * Layout: every per-agent tensor is agent-major, env-minor: X[agent][env][feature]
  * (so an agent's rows are contiguous for its grouped GEMM, and the env kernel is coalesced
@@ -85,10 +88,16 @@ typedef struct {
 
 const char* nmarl_last_error(void);
 int nmarl_version(void);
+/* ---- context: owns the helper stream/events of the CURRENT device; no other state ---------- */
+typedef struct nmarl_ctx nmarl_ctx;
+int nmarl_create(nmarl_ctx** out);
+int nmarl_destroy(nmarl_ctx* ctx);
 /* size-of checks so the ctypes mirror can assert its struct layout */
 int nmarl_sizeof_model(void);
 int nmarl_sizeof_agent(void);
 int nmarl_sizeof_cacc_cfg(void);
+int nmarl_sizeof_fwd_args(void);
+int nmarl_sizeof_bwd_args(void);
 
 /* ---- K1: environment ---------------------------------------------------------------------
  * Replaces CACCEnv.reset/_init_catchup/_init_slowdown (envs/cacc_env.py:166-189,285-318) and
@@ -207,6 +216,13 @@ typedef struct {
                                 [T][N][feature][B] and sv_dpre is unused.                                          */
   int32_t state_fm;          /* tensor-core path only: h_seq / c_seq / msg_seq / dh_rec / dc_rec / dmsg are
                                 feature-major ([..][64][B] instead of [..][B][64])                                  */
+  nmarl_ctx* ctx;            /* required by nmarl_a2c_bptt / nmarl_a2c_backward (forked side work)                  */
+  int32_t raw_tiles;         /* tensor-core path: sv_dzT / sv_dpT hold ONE raw fp32 tile per 32 rows (the weight-
+                                gradient kernel derives the 3xTF32 `lo` part in shared memory) instead of a
+                                [hi | lo] pair: half the operand-tile traffic                                       */
+  void** ev_step;            /* optional timing hooks (bench.py): 2*T cudaEvent_t, recorded on `stream` before /
+                                after the cell kernel of reverse step t at [2t], [2t+1]; NULL = none               */
+  void** ev_wgrad;           /* optional: 2 cudaEvent_t around the weight-gradient GEMM kernel; NULL = none         */
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */

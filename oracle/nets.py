@@ -277,17 +277,10 @@ class OraclePolicy:
             return [[n for n in self.names if n.startswith('lstm_%d/' % i)] for i in range(self.N)]
         return [self.names]
 
-    def backward(self, obs, ps, acts, dones, Rs, Advs, lr, v_coef=0.5, e_coef=0.05,
-                 max_grad_norm=40.0, alpha=0.99, epsilon=1e-5, apply=True):
-        """Rs/Advs in [T,B,N] layout.  Returns dict of summaries; grads kept in self.grads."""
-        for t in self.p.values():
-            t.grad = None
-        pi, v = self.unroll(obs, ps, acts, dones, self.states_bw)
-        p_loss, v_loss, e_loss = self.loss_terms(pi, v, acts, Rs, Advs, v_coef, e_coef)
-        loss = p_loss.sum() + v_loss.sum() + e_loss.sum()
-        loss.backward()
-        self.grads = {n: (self.p[n].grad.detach().clone() if self.p[n].grad is not None
-                          else torch.zeros_like(self.p[n])) for n in self.names}
+    def apply_grads(self, lr, max_grad_norm=40.0, alpha=0.99, epsilon=1e-5, apply=True):
+        """clip_by_global_norm + TF RMSProp on ``self.grads`` (policies.py:34-39, 257-264); one group per agent for
+        IA2C.  Returns the group norms.  Split out of ``backward`` so that tests can accumulate ``self.grads`` over
+        env chunks of a large batch before the (single) optimizer step."""
         norms = []
         with torch.no_grad():
             for group in self._groups():
@@ -301,6 +294,20 @@ class OraclePolicy:
                         self.p[n].sub_(lr * g / torch.sqrt(self.ms[n] + epsilon))
             if apply and self.variant == 'ma2c_cu':
                 self.consensus_update()
+        return norms
+
+    def backward(self, obs, ps, acts, dones, Rs, Advs, lr, v_coef=0.5, e_coef=0.05,
+                 max_grad_norm=40.0, alpha=0.99, epsilon=1e-5, apply=True):
+        """Rs/Advs in [T,B,N] layout.  Returns dict of summaries; grads kept in self.grads."""
+        for t in self.p.values():
+            t.grad = None
+        pi, v = self.unroll(obs, ps, acts, dones, self.states_bw)
+        p_loss, v_loss, e_loss = self.loss_terms(pi, v, acts, Rs, Advs, v_coef, e_coef)
+        loss = p_loss.sum() + v_loss.sum() + e_loss.sum()
+        loss.backward()
+        self.grads = {n: (self.p[n].grad.detach().clone() if self.p[n].grad is not None
+                          else torch.zeros_like(self.p[n])) for n in self.names}
+        norms = self.apply_grads(lr, max_grad_norm, alpha, epsilon, apply=apply)
         self.states_bw = self.states_fw.clone()
         self.last_pi, self.last_v = pi.detach(), v.detach()
         return dict(policy_loss=p_loss.detach().numpy(), value_loss=v_loss.detach().numpy(),

@@ -1,4 +1,4 @@
-"""GPU (opt-in until it has been run once on hardware: NMARL_RUN_TFNET_GPU=1): the drop-in path -- CUDA env, agent
+"""GPU: the drop-in path -- CUDA env, agent
 classes, Trainer -- directly against the traces of the UNMODIFIED reference executed on the TF shim
 (tests/golden/tfnet_*.npz, see tests/test_tfnet_parity.py), without the oracle in between: same initial weights
 from the same NumPy stream, every pi / v / bootstrap R within 1e-5, same logged rewards, trained weights within 2e-5."""
@@ -10,8 +10,7 @@ import pytest
 
 from helpers import golden, load_cfg
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('NMARL_RUN_TFNET_GPU') != '1', reason='opt-in: set NMARL_RUN_TFNET_GPU=1')]
+pytestmark = pytest.mark.gpu
 
 CASES = ['tfnet_ma2c_nc_catchup', 'tfnet_ia2c_slowdown', 'tfnet_ia2c_fp_catchup', 'tfnet_ma2c_ic3_slowdown',
          'tfnet_ma2c_dial_catchup', 'tfnet_ma2c_cu_catchup']
