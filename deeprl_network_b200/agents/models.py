@@ -216,7 +216,8 @@ class IA2C:
         self.engine.rollout(env, **kw)
 
     def update(self):
-        self.engine.update(self.lr_scheduler.get(self.n_step))
+        # the schedule counts environment steps: n_step steps of every env on every rank per update
+        self.engine.update(self.lr_scheduler.get(self.n_step * self.n_env * self.engine.world))
 
 
 class IA2C_FP(IA2C):

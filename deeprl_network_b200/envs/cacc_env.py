@@ -183,9 +183,12 @@ class CACCEnv:
         # NB the reference tests the already-incremented attribute (cacc_env.py:290,311); the only
         # config seed reaching the deterministic branch (-1) is rejected by np.random.seed above.
         u = np.random.rand()
-        if self.n_env > 1 or self._u01.shape[0] > 1:
+        if self.n_env > 1:
             self.reset_device(u01=None, philox_seed=seed)
-        self._u01[0, 0] = u
+            self.episode_dev[0] -= 1          # env 0 is reset again below; count its episode once
+        # env 0: the reference's single np.random.rand(); further platoons (grid stub only) draw their own
+        self._u01[:, 0] = torch.as_tensor([u] + [np.random.rand() for _ in range(self._u01.shape[0] - 1)],
+                                          dtype=torch.float64)
         self.reset_device(u01=self._u01, mask=self._mask0)
         self.collision = False
         self.t = 0

@@ -282,6 +282,13 @@ class VecTrainer:
         self.graph = None
         self.n_update = 0
         self.env.train_mode = True
+        # Episodes end (env `done`) only at multiples of the env's batch_size and at T: the per-env auto-reset below
+        # looks at the done flag of the LAST step of an update only, so updates must tile the episode exactly
+        # (the reference's Trainer has the same requirement implicitly, utils.py:129-197).
+        if env.T % model.n_step or env.batch_size % model.n_step:
+            raise AssertionError('VecTrainer: episode length %d / env batch_size %d are not multiples of the update '
+                                 'length %d' % (env.T, env.batch_size, model.n_step))
+        self.data = []                     # one record per update (train_reward.csv of the batched loop)
 
     def start(self):
         self._seed = self.env.seed
@@ -302,7 +309,9 @@ class VecTrainer:
 
     def update(self, uniforms=None):
         e = self.engine
-        lr = self.model.lr_scheduler.get(self.model.n_step)
+        # the schedule counts ENVIRONMENT steps (main.py's total_step): one update consumes n_step steps of every
+        # env on every rank, so a linear lr_decay reaches lr_min at total_step whatever n_env / world size is
+        lr = self.model.lr_scheduler.get(self.model.n_step * self.env.n_env * e.world)
         e.lr_dev.fill_(float(lr))
         self._lr = e.lr_dev
         if not self.use_graph:
@@ -324,3 +333,18 @@ class VecTrainer:
     def mean_reward(self):
         """Mean per-step global reward of the last batch (host sync)."""
         return float(self.engine.grew_buf[:self.engine.T_cur].mean().item())
+
+    def log_rewards(self, global_step, summary_writer=None):
+        """One `train_reward.csv` record (same columns as Trainer._log_episode): mean / std of the per-step global
+        reward over the last batch of every env.  Unlike the one-env Trainer (quirk Q4) no greedy test episode is
+        interleaved: these are the TRAINING rewards.  Host sync."""
+        g = self.engine.grew_buf[:self.engine.T_cur]
+        mean, std = float(g.mean().item()), float(g.std(unbiased=False).item())
+        self.data.append(dict(agent=self.env.agent, step=int(global_step), test_id=-1, avg_reward=mean, std_reward=std))
+        if summary_writer is not None:
+            summary_writer.add_scalar('train_reward', mean, int(global_step))
+        return mean
+
+    def write_csv(self, output_path):
+        import pandas as pd
+        pd.DataFrame(self.data).to_csv(output_path + 'train_reward.csv')

@@ -65,16 +65,22 @@ def init_agent(env, config, total_step, seed, **kw):
                              total_step, config, seed=seed, n_env=env.n_env, **kw)
 
 
-def _train_batched(env, model, total_step):
-    """n_env > 1: whole updates on the device until total_step environment steps (summed over envs) are done."""
+def _train_batched(env, model, total_step, log_interval, writer=None, output_path=None):
+    """n_env > 1: whole updates on the device until total_step environment steps (summed over envs) are done.
+    Every `log_interval` environment steps one record goes to data/train_reward.csv (and the TB scalar
+    `train_reward`): mean / std of the per-step global TRAINING reward of the last batch."""
     loop = U.VecTrainer(env, model)
     loop.start()
-    done_steps = 0
+    done_steps, per_update = 0, model.n_step * env.n_env
+    every = max(1, int(log_interval) // per_update)
     while done_steps < total_step:
         loop.update()
-        done_steps += model.n_step * env.n_env
-        if loop.n_update % 10 == 0:
-            logging.info('update %d, env steps %d, mean step reward %.2f' % (loop.n_update, done_steps, loop.mean_reward()))
+        done_steps += per_update
+        if loop.n_update % every == 0 or done_steps >= total_step:
+            r = loop.log_rewards(done_steps, writer)
+            logging.info('update %d, env steps %d, mean step reward %.2f' % (loop.n_update, done_steps, r))
+    if output_path is not None:
+        loop.write_csv(output_path)
     return done_steps
 
 
@@ -90,7 +96,8 @@ def train(args):
     if model is None:
         raise SystemExit(2)
     if env.n_env > 1:
-        final_step = _train_batched(env, model, steps['total_step'])
+        final_step = _train_batched(env, model, steps['total_step'], steps['log_interval'],
+                                    U.make_summary_writer(dirs['log']), dirs['data'])
     else:
         counter = U.Counter(steps['total_step'], steps['test_interval'], steps['log_interval'])
         U.Trainer(env, model, counter, U.make_summary_writer(dirs['log']), output_path=dirs['data']).run()
