@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..layout import ModelLayout
+from ..layout import HeteroLayout, ModelLayout
 from .engine import PolicyEngine
 from .utils import Scheduler
 
@@ -36,10 +36,16 @@ class IA2C:
     def _init_algo(self, n_s_ls, n_a_ls, neighbor_mask, distance_mask, coop_gamma, total_step, seed,
                    model_config, n_env, device, obs_mode, flat_params):
         self.n_s_ls, self.n_a_ls = list(n_s_ls), list(n_a_ls)
-        if max(self.n_a_ls) != min(self.n_a_ls):
-            raise NotImplementedError('heterogeneous action spaces (lstm_*_hetero) are outside the hot path')
-        self.identical_agent = True
-        self.n_s, self.n_a = self.n_s_ls[0], self.n_a_ls[0]
+        # agents/models.py:89-97: agents are "identical" iff all action spaces are equal; otherwise inputs are
+        # zero-padded to the widest agent and the *_hetero layers slice each agent's valid part
+        self.identical_agent = max(self.n_a_ls) == min(self.n_a_ls)
+        if self.identical_agent:
+            self.n_s, self.n_a = self.n_s_ls[0], self.n_a_ls[0]
+        else:
+            if self.variant not in ('ma2c_nc', 'ma2c_ic3', 'ma2c_dial'):
+                raise NotImplementedError('heterogeneous action spaces are covered for ma2c_nc / ma2c_ic3 / ma2c_dial '
+                                          '(lstm_comm_hetero / lstm_ic3_hetero / lstm_dial_hetero)')
+            self.n_s, self.n_a = max(self.n_s_ls), max(self.n_a_ls)
         self.neighbor_mask = np.asarray(neighbor_mask)
         self.n_agent = len(self.neighbor_mask)
         self.reward_clip = model_config.getfloat('reward_clip')
@@ -53,8 +59,12 @@ class IA2C:
             obs_mode = 'concat' if self.variant == 'ia2c' else 'gather'
         if self.variant == 'ia2c_fp':     # "neighborhood policies are included in local state" (agents/models.py:172-177)
             self.n_s_ls = [n + self.n_a * int(np.sum(self.neighbor_mask[i])) for i, n in enumerate(self.n_s_ls)]
-        self.layout = ModelLayout(self.variant, self.n_s_ls, self.n_a, self.neighbor_mask,
-                                  n_h=self.n_lstm, n_fc=self.n_fc, obs_mode=obs_mode)
+        if self.identical_agent:
+            self.layout = ModelLayout(self.variant, self.n_s_ls, self.n_a, self.neighbor_mask,
+                                      n_h=self.n_lstm, n_fc=self.n_fc, obs_mode=obs_mode)
+        else:
+            self.layout = HeteroLayout(self.variant, self.n_s_ls, self.n_a_ls, self.neighbor_mask,
+                                       n_h=self.n_lstm, n_fc=self.n_fc)
         self.nbr = self.layout.nbr
         hp = dict(v_coef=0.5, e_coef=0.01, max_grad_norm=40.0, alpha=0.99, epsilon=1e-5, gamma=0.99,
                   reward_norm=self.reward_norm, reward_clip=self.reward_clip)
@@ -88,8 +98,8 @@ class IA2C:
         out = np.zeros((self.n_agent, S), dtype=np.float32)
         for i in range(self.n_agent):
             o = np.asarray(obs[i], dtype=np.float32).ravel()
-            w = self.layout.base_n_s if self.layout.obs_mode == 'gather' else len(o)
-            out[i, :w] = o[:w]
+            w = min(len(o), self.layout.base_n_s) if self.layout.obs_mode == 'gather' else len(o)
+            out[i, :w] = o[:w]              # shorter rows (heterogeneous agents) stay zero-padded (agents/models.py:229-235)
         return out
 
     def _upload_step(self, obs, done, ps):
@@ -98,7 +108,7 @@ class IA2C:
         s['obs'].copy_(torch.from_numpy(self._pack_obs(obs))[:, None, :])
         s['done'].fill_(float(bool(done)))
         if ps is not None:
-            s['fp'].copy_(torch.as_tensor(np.asarray(ps, dtype=np.float32))[:, None, :])
+            s['fp'].copy_(torch.as_tensor(self._pad_ps(ps))[:, None, :])
 
     # ---- reference API ---------------------------------------------------------------------------------
     def forward(self, obs, done, nactions=None, out_type='p'):
@@ -123,6 +133,17 @@ class IA2C:
     def _ps_from_obs(self, obs):
         """Fingerprints carried inside the observation (only IA2C_FP has them)."""
         return None
+
+    def _pad_ps(self, ps):
+        """[N, n_a] float32; heterogeneous agents hand over a list of per-agent policies of different lengths,
+        zero-padded to the widest action space (agents/models.py:229-235)."""
+        if self.identical_agent:
+            return np.asarray(ps, dtype=np.float32)
+        out = np.zeros((self.n_agent, self.n_a), dtype=np.float32)
+        for i, q in enumerate(ps):
+            q = np.asarray(q, dtype=np.float32).ravel()
+            out[i, :len(q)] = q
+        return out
 
     def add_transition(self, ob, naction, action, reward, value, done):
         """agents/models.py:26-32 (reward norm/clip happen inside the returns kernel)."""
@@ -248,14 +269,17 @@ class MA2C_NC(IA2C):
         self._upload_step(obs, done, ps)
         if out_type.startswith('p'):
             e.step_p(s['obs'], s['fp'], s['done'], e.pi_tmp)
-            return e.pi_tmp[:, 0].cpu().numpy()
+            pi = e.pi_tmp[:, 0].cpu().numpy()
+            if self.identical_agent:
+                return pi
+            return [pi[i, :self.n_a_ls[i]] for i in range(self.n_agent)]     # pi_ls of agents/policies.py:296
         s['act'].copy_(torch.as_tensor(np.asarray(actions, dtype=np.int32))[:, None])
         e.step_v(s['obs'], s['fp'], s['done'], s['act'], s['v'])
         return s['v'][:, 0].cpu().numpy()
 
     def add_transition(self, ob, p, action, reward, value, done):
         """agents/models.py:198-209"""
-        self._obs.append(self._pack_obs(ob)); self._ps.append(np.asarray(p, dtype=np.float32))
+        self._obs.append(self._pack_obs(ob)); self._ps.append(self._pad_ps(p))
         self._acts.append(np.asarray(action, dtype=np.int32)); self._rs.append(reward)
         self._vs.append(np.asarray(value, dtype=np.float32)); self._dones.append(bool(done))
 

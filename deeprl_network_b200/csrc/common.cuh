@@ -49,6 +49,22 @@ void nmarl_set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
+// ---- kernel launch with optional programmatic dependent launch (see tc.cuh: pdl_wait) ---------------------------
+// NMARL_NO_PDL=1 in the environment turns the attribute off (A/B switch; the device-side instructions become no-ops).
+bool nmarl_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t nmarl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && nmarl_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- cp.async (LDGSTS) staging ------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -107,6 +107,10 @@ __global__ void cacc_step_kernel(const EnvK k, int train_mode, const int32_t* __
                                  const double* __restrict__ v_init, float* obs, int obs_stride, double* reward,
                                  double* greward, float* done) {
   extern __shared__ double sm_env[];                 // [2][N][32]: per-agent reward, new headway
+  // programmatic dependent launch: the CTAs may already be resident while the policy call that produces `action`
+  // finishes; let the next policy call's CTAs start their prologue as well
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const nmarl_cacc_cfg& c = k.c;
   const int N = c.n_agent, L = c.platoon_len, B = k.B;
   const int e = threadIdx.x, i = threadIdx.y;
@@ -228,8 +232,8 @@ extern "C" int nmarl_cacc_step(const nmarl_cacc_cfg* cfg, int B, int train_mode,
   EnvK k{*cfg, B};
   const dim3 blk(32, cfg->n_agent);
   const size_t smem = (size_t)2 * cfg->n_agent * 32 * sizeof(double);
-  cacc_step_kernel<<<(B + 31) / 32, blk, smem, (cudaStream_t)stream>>>(k, train_mode, action, hs, vs, us, t, collision,
-                                                                     v_init, obs, obs_stride, reward, greward, done);
+  NMARL_CUDA(nmarl_launch(cacc_step_kernel, dim3((B + 31) / 32), blk, smem, (cudaStream_t)stream, true, k, train_mode,
+                          action, hs, vs, us, t, collision, v_init, obs, obs_stride, reward, greward, done));
   NMARL_LAUNCH_CHECK();
   return 0;
 }

@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
-  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
-  uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
+  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + A_SLOTS;
+  uint64_t* enc_full = a_empty + A_SLOTS, *acc_full = enc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
   KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int n_kb = *n_kb_s;
+  tc::pdl_launch_dependents();       // PDL (tc.cuh): the prologue overlapped the previous reverse step's tail
+  tc::pdl_wait();
 
   if (warp < ROW_THREADS / 32) {
     RowCtx c;
@@ -265,7 +267,7 @@ int launch_tc_bwd_fm(const nmarl_model* m, const BwdK& k, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(k.B / 128, m->n_agent);
-  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k);
+  NMARL_CUDA(nmarl_launch(kern, grid, dim3(TC_THREADS), TC_SMEM, st, true, *m, k));
   NMARL_LAUNCH_CHECK();
   return 0;
 }

@@ -13,8 +13,8 @@
 //              128B-swizzled [hi | lo] weight tiles into a 3-stage shared-memory ring (mbarrier tx).
 //   warp 17    MMA issuer: a single elected thread issues tcgen05.mma kind::tf32 (3 per k-step:
 //              hi*hi + hi*lo + lo*hi) and tcgen05.commit's completion onto the ring barriers.
-// TMEM (512 columns): [0,256) gate accumulator, [256,320) encoder accumulator, [320,448) A-operand
-// ring (2 slots x (hi 32 | lo 32)).
+// TMEM (512 columns): [0,256) accumulators (the encoder GEMMs land in 64-column blocks of it and are consumed
+// before the gate GEMM overwrites it), [256,512) A-operand ring (4 slots x (hi 32 | lo 32)).
 //
 // Same math, same argument block and same outputs as cell_fwd.cu (FP32 FFMA); used when
 // B % 128 == 0 and packed weights are supplied.  Restates the same reference lines as cell_fwd.cu.
@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
-  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
-  uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
+  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + A_SLOTS;
+  uint64_t* enc_full = a_empty + A_SLOTS, *acc_full = enc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
   KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const int n_kb = *n_kb_s;
+  // PDL: the prologue above overlapped the tail of the previous kernel of the stream; from here on the kernel reads
+  // what that kernel (env step / previous cell call) wrote.
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();
 
   if (warp < ROW_THREADS / 32) {
     // =================================== row threads ===================================================
@@ -481,7 +485,7 @@ int launch_tc_fm(const nmarl_model* m, const FwdK& k, cudaStream_t st) {
   dim3 grid(k.a.B / 128, m->n_agent);
   FwdK k2 = k;
   k2.prof = g_nmarl_prof;
-  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(*m, k2);
+  NMARL_CUDA(nmarl_launch(kern, grid, dim3(TC_THREADS), TC_SMEM, st, true, *m, k2));
   NMARL_LAUNCH_CHECK();
   return 0;
 }

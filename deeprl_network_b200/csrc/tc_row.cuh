@@ -9,7 +9,12 @@ namespace tcrow {
 
 constexpr int S_STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 2 * 256 * 128;          // hi+lo tiles of the widest operand (N = 256)
-constexpr uint32_t ACC_COL = 0, A_COL = 256;            // TMEM: [0,256) accumulators (encoders reuse it), [256,384) A ring
+constexpr uint32_t ACC_COL = 0, A_COL = 256;            // TMEM: [0,256) accumulators (encoders reuse it), [256,512) A ring
+// A-operand ring in TMEM: A_SLOTS slots of (hi 32 | lo 32) columns.  4 slots use the whole second half of TMEM; the row
+// threads then run up to four k-blocks ahead of the MMA issuer, which matters for the short encoder GEMMs whose
+// MMAs (N = 64) finish faster than a produce -> commit -> a_empty round trip.
+constexpr int A_SLOTS = 4;
+static_assert((A_SLOTS & (A_SLOTS - 1)) == 0 && A_COL + A_SLOTS * 64 <= 512, "A ring must fit TMEM");
 constexpr int MAX_KB = 40;
 // NSET warp-sets share every env row: set s of row r works on columns [s*W, (s+1)*W) of each 32-wide input
 // k-block and on hidden units [s*EW, (s+1)*EW) of the encoders / LSTM cell.  4 sets = 16 row warps per SM
@@ -34,18 +39,18 @@ struct RowCtx {
 };
 
 __device__ __forceinline__ void produce_begin(RowCtx& c) {
-  const int slot = c.q & 1;
-  tc::mbar_wait(&c.a_empty[slot], ((c.q >> 1) & 1) ^ 1, c.err, 11);
+  const int slot = c.q & (A_SLOTS - 1);
+  tc::mbar_wait(&c.a_empty[slot], ((c.q / A_SLOTS) & 1) ^ 1, c.err, 11);
   tc::fence_after_sync();
 }
 __device__ __forceinline__ void produce_piece(RowCtx& c, int col /*0..31, multiple of 8*/, const float (&x)[8]) {
-  const uint32_t t = c.tmem + c.lane_base + A_COL + (c.q & 1) * 64 + col;
+  const uint32_t t = c.tmem + c.lane_base + A_COL + (c.q & (A_SLOTS - 1)) * 64 + col;
   tc::tmem_st_hilo8(t, t + 32, x);
 }
 __device__ __forceinline__ void produce_end(RowCtx& c) {
   tc::wait_st();
   tc::fence_before_sync();
-  tc::mbar_arrive(&c.a_full[c.q & 1]);
+  tc::mbar_arrive(&c.a_full[c.q & (A_SLOTS - 1)]);
   c.q++;
 }
 // one input k-block: this thread contributes columns [set*W, set*W + W)
@@ -181,11 +186,11 @@ __device__ __forceinline__ void mma_loop(const KbEnt* sched, int n_kb, uint8_t* 
                                          uint64_t* a_full, uint64_t* a_empty, uint64_t* enc_full, uint64_t* acc_full,
                                          uint32_t tmem, int* err, long long* prof = nullptr) {
   for (int q = 0; q < n_kb; ++q) {
-    const int st = q % S_STAGES, slot = q & 1;
+    const int st = q % S_STAGES, slot = q & (A_SLOTS - 1);
     const KbEnt e = sched[q];
     tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, err, 31);
     if (prof) prof[32 + 3 * q] = clock64();
-    tc::mbar_wait(&a_full[slot], (q >> 1) & 1, err, 32);
+    tc::mbar_wait(&a_full[slot], (q / A_SLOTS) & 1, err, 32);
     tc::fence_after_sync();
     if (prof) prof[33 + 3 * q] = clock64();
     const uint32_t tile = e.bytes / 2;
@@ -216,6 +221,6 @@ __device__ __forceinline__ KbEnt make_kb(int off_floats, int N, int K, int kb, i
   e.pad0 = e.pad1 = 0;
   return e;
 }
-constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 16 * 8 + 16 + MAX_KB * sizeof(KbEnt) + NSET * 128 * 8 * sizeof(float);
+constexpr size_t TC_SMEM = S_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 32 * 8 /*mbarriers*/ + 16 + MAX_KB * sizeof(KbEnt) + NSET * 128 * 8 * sizeof(float);
 
 }  // namespace tcrow

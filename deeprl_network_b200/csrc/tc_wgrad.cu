@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
-  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + 2;
-  uint64_t* enc_full = a_empty + 2, *acc_full = enc_full + 1;
+  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + A_SLOTS;
+  uint64_t* enc_full = a_empty + A_SLOTS, *acc_full = enc_full + 1;
   uint64_t* lo_full = acc_full + 1;                                    // RAW only: S_STAGES barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1 + (RAW ? S_STAGES : 0));
 
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     if constexpr (RAW)
@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)d.N);
       for (int q = 0; q < nkb; ++q) {
-        const int st = q % S_STAGES, slot = q & 1;
+        const int st = q % S_STAGES, slot = q & (A_SLOTS - 1);
         tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 31);
-        tc::mbar_wait(&a_full[slot], (q >> 1) & 1, k.err, 32);
+        tc::mbar_wait(&a_full[slot], (q / A_SLOTS) & 1, k.err, 32);
         tc::fence_after_sync();
         const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile_bytes);
         if constexpr (RAW) {

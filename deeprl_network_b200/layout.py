@@ -288,3 +288,114 @@ class ModelLayout:
 
     def n_real_param(self):
         return int(sum(np.prod(s) for _, _, s in self.entries))
+
+
+PI_PAD_BIAS = -1.0e30      # bias of a padded (non-existent) action: softmax gives it probability exactly 0
+
+
+class HeteroLayout(ModelLayout):
+    """Agents with UNEQUAL observation / action widths (the reference's ``identical_agent == False`` path:
+    lstm_comm_hetero / lstm_ic3_hetero / lstm_dial_hetero, agents/utils.py:220-341, 420-512, 602-702; per-agent
+    heads, agents/policies.py:289-312; zero-padded inputs, agents/models.py:229-235).
+
+    The kernels stay homogeneous: the model is EMBEDDED in a padded one with ``n_s = max(n_s_ls)`` and
+    ``n_a = max(n_a_ls)`` for everybody.  Every reference tensor (tight shape, reference name, reference creation
+    order) maps onto a sub-block of the padded tensor; the rest of the padded tensor is zero and provably stays zero:
+      * padded observation / fingerprint inputs are 0, so the weight rows they meet get gradient x^T d = 0;
+      * a padded action has policy-head bias PI_PAD_BIAS and zero weights -> pi = exp(-1e30 - max) = 0 exactly,
+        d(logit) = pi * (g - <pi, g>) = 0, it is never sampled (its cdf step has zero width) and never the arg-max;
+      * value-head rows of padded actions are never selected by a one-hot;
+      * an agent without neighbours keeps zero message / fingerprint encoders (relu(0) = 0 feeds the gate GEMM
+        zeros and receives zero gradients -- the same argument as for ia2c_fp, see the module docstring).
+    Zero gradients leave clip-by-global-norm and RMSProp untouched, so pi, v, gradients and trained weights equal
+    the reference's tight model.  pack / unpack / creation_order / checkpoints speak the reference's tight tensors.
+    """
+
+    def __init__(self, variant, n_s_ls, n_a_ls, neighbor_mask, n_h=64, n_fc=64):
+        if variant not in SCOPE:
+            raise ValueError('heterogeneous agents exist for ma2c_nc / ma2c_ic3 / ma2c_dial only (got %r)' % variant)
+        self.tight_n_s, self.tight_n_a = [int(x) for x in n_s_ls], [int(x) for x in n_a_ls]
+        ns_max, na_max = max(self.tight_n_s), max(self.tight_n_a)
+        super().__init__(variant, [ns_max] * len(self.tight_n_s), na_max, neighbor_mask, n_h=n_h, n_fc=n_fc, obs_mode='gather')
+        if variant == 'ma2c_ic3' and min(len(x) for x in self.nbr) == 0:
+            raise NotImplementedError('CommNet agent without neighbours (mean over an empty set) is not supported')
+        self.hetero = True
+        self._embed()
+
+    def _embed(self):
+        v, N, ns_max, na_max = self.variant, self.N, self.base_n_s, self.n_a
+        pad = {n: (o, s) for n, o, s in self.entries}           # padded tensors of the inner homogeneous layout
+        tight, idx = [], {}
+
+        def rows(name, new_name, row_ids, ncol):
+            """tight tensor = the listed rows of padded tensor `name` (all `ncol` columns)."""
+            o, shp = pad[name]
+            pc = shp[1] if len(shp) == 2 else 1
+            r = np.asarray(row_ids, dtype=np.int64)
+            idx[new_name] = (o + r[:, None] * pc + np.arange(ncol)[None, :]).ravel()
+            tight.append((new_name, (len(r), ncol)))
+
+        def vec(name, n=None):
+            o, shp = pad[name]
+            n = shp[0] if n is None else n
+            idx[name] = o + np.arange(n, dtype=np.int64)
+            tight.append((name, (n,)))
+
+        sc, cell = SCOPE[v], CELL[v]
+        for i in range(N):
+            s = '%s/%s_%d' % (sc, cell, i)
+            nb = self.nbr[i]
+            x_rows = [f for f in range(self.tight_n_s[i])] + [(k + 1) * ns_max + f for k, j in enumerate(nb) for f in range(self.tight_n_s[j])]
+            p_rows = [k * na_max + a for k, j in enumerate(nb) for a in range(self.tight_n_a[j])]
+            km = NH if v == 'ma2c_ic3' else NH * len(nb)
+            if v == 'ma2c_nc':           # creation order of lstm_comm_hetero: w_ob first (agents/utils.py:260-283)
+                rows(s + '/w_ob', s + '/w_ob', x_rows, NH); vec(s + '/b_ob')
+                if nb:
+                    rows(s + '/w_fp', s + '/w_fp', p_rows, NH); vec(s + '/b_fp')
+                    rows(s + '/w_msg', s + '/w_msg', range(km), NH); vec(s + '/b_msg')
+                rows(s + '/wx_hid', s + '/wx_hid', range(3 * NH if nb else NH), 4 * NH)
+            else:
+                if nb:
+                    rows(s + '/w_msg', s + '/w_msg', range(km), NH); vec(s + '/b_msg')
+                rows(s + '/w_ob', s + '/w_ob', x_rows, NH); vec(s + '/b_ob')
+                rows(s + '/wx_hid', s + '/wx_hid', range(NH), 4 * NH)
+            rows(s + '/wh_hid', s + '/wh_hid', range(NH), 4 * NH); vec(s + '/b_hid')
+        if v == 'ma2c_dial':
+            for i in range(N):
+                rows('dial/mfc_%d/w' % i, 'dial/mfc_%d/w' % i, range(NH), NH); vec('dial/mfc_%d/b' % i)
+        self.pi_pad = []
+        for i in range(N):
+            hp, hv = '%s/pi_%d' % (sc, i), '%s/v_%d' % (sc, i)
+            na = self.tight_n_a[i]
+            o, _ = pad[hp + '/w']
+            idx[hp + '/w'] = (o + np.arange(NH)[:, None] * na_max + np.arange(na)[None, :]).ravel()
+            tight.append((hp + '/w', (NH, na)))
+            vec(hp + '/b', na)
+            ob, _ = pad[hp + '/b']
+            self.pi_pad += [ob + a for a in range(na, na_max)]
+            v_rows = list(range(NH)) + [NH + k * na_max + a for k, j in enumerate(self.nbr[i]) for a in range(self.tight_n_a[j])]
+            rows(hv + '/w', hv + '/w', v_rows, 1); vec(hv + '/b')
+        self._idx, self._tight = idx, tight
+        self._tight_shapes = dict(tight)
+        # `entries` is what callers enumerate (names, shapes, checkpoints): reference tensors; offset = first element
+        self.entries = [(n, int(idx[n][0]) if len(idx[n]) else 0, s) for n, s in tight]
+        self.by_name = {n: (o, s) for n, o, s in self.entries}
+
+    def creation_order(self):
+        return list(self._tight)          # built in tf.get_variable order (cells, [mfc], heads)
+
+    def pack(self, params):
+        flat = np.zeros(self.n_param, dtype=np.float32)
+        flat[self.pi_pad] = PI_PAD_BIAS
+        for name, shape in self._tight:
+            a = np.asarray(params[name], dtype=np.float32)
+            assert a.shape == shape, (name, a.shape, shape)
+            flat[self._idx[name]] = a.ravel()
+        return flat
+
+    def unpack(self, flat):
+        flat = np.asarray(flat)
+        return {name: flat[self._idx[name]].reshape(shape).copy() for name, shape in self._tight}
+
+    def n_real_param(self):
+        return int(sum(np.prod(s) for _, s in self._tight))

@@ -13,6 +13,9 @@ This file is a line-by-line restatement of
   * ``lstm_comm``     agents/utils.py:118-217      (NeurComm)
   * ``lstm_ic3``      agents/utils.py:344-417      (CommNet)
   * ``lstm_dial``     agents/utils.py:515-599      (DIAL)
+  * ``lstm_comm_hetero`` / ``lstm_ic3_hetero`` / ``lstm_dial_hetero``  agents/utils.py:220-341, 420-512, 602-702
+    (agents with unequal observation / action widths: pass ``n_a`` as a list; pinned by tests/golden/hetero_*.npz,
+    which ran the unmodified reference classes on the TF shim)
   * heads             agents/policies.py:50-77, 291-312
   * loss              agents/policies.py:20-39 (IA2C, per agent) / :232-264 (MA2C)
   * stateful forward/backward protocol  agents/policies.py:103-134, 200-230, 334-336
@@ -37,6 +40,11 @@ def ortho_init(shape, scale=np.sqrt(2)):
     u, _, v = np.linalg.svd(a, full_matrices=False)
     q = u if u.shape == tuple(shape) else v
     return (scale * q.reshape(shape)).astype(np.float32)
+
+
+def is_hetero(n_a):
+    """n_a given per agent with unequal entries (agents/models.py:89-97: identical_agent iff all n_a equal)."""
+    return (not np.isscalar(n_a)) and len(set(int(a) for a in n_a)) > 1
 
 
 def param_shapes(variant, n_s_ls, n_a, mask, n_h=64, n_fc=64):
@@ -71,6 +79,33 @@ def param_shapes(variant, n_s_ls, n_a, mask, n_h=64, n_fc=64):
                     ('cu/v_%da/w' % i, (n_h + n_a * nm[i], 1)), ('cu/v_%da/b' % i, (1,))]
         return out
     sc, cell = SCOPE[variant], CELL[variant]
+    if is_hetero(n_a):
+        # lstm_*_hetero: tight per-agent widths; NeurComm creates w_ob FIRST here (agents/utils.py:260-283), agents
+        # without neighbours have no message / fingerprint encoder and a [n_h, 4 n_h] wx_hid
+        n_a_ls = [int(a) for a in n_a]
+        nbr = [list(np.where(np.asarray(mask)[i] == 1)[0]) for i in range(N)]
+        for i in range(N):
+            s = '%s/%s_%d' % (sc, cell, i)
+            kx = n_s_ls[i] + sum(n_s_ls[j] for j in nbr[i])
+            kp = sum(n_a_ls[j] for j in nbr[i])
+            if variant == 'ma2c_nc':
+                out += [(s + '/w_ob', (kx, n_h)), (s + '/b_ob', (n_h,))]
+                if nm[i]:
+                    out += [(s + '/w_fp', (kp, n_h)), (s + '/b_fp', (n_h,)),
+                            (s + '/w_msg', (n_h * nm[i], n_h)), (s + '/b_msg', (n_h,))]
+                out += [(s + '/wx_hid', ((3 if nm[i] else 1) * n_h, 4 * n_h)), (s + '/wh_hid', (n_h, 4 * n_h)), (s + '/b_hid', (4 * n_h,))]
+            else:
+                if nm[i]:
+                    out += [(s + '/w_msg', (n_h if variant == 'ma2c_ic3' else n_h * nm[i], n_h)), (s + '/b_msg', (n_h,))]
+                out += [(s + '/w_ob', (kx, n_h)), (s + '/b_ob', (n_h,)),
+                        (s + '/wx_hid', (n_h, 4 * n_h)), (s + '/wh_hid', (n_h, 4 * n_h)), (s + '/b_hid', (4 * n_h,))]
+        if variant == 'ma2c_dial':
+            for i in range(N):
+                out += [('%s/mfc_%d/w' % (sc, i), (n_h, n_h)), ('%s/mfc_%d/b' % (sc, i), (n_h,))]
+        for i in range(N):
+            out += [('%s/pi_%d/w' % (sc, i), (n_h, n_a_ls[i])), ('%s/pi_%d/b' % (sc, i), (n_a_ls[i],)),
+                    ('%s/v_%d/w' % (sc, i), (n_h + sum(n_a_ls[j] for j in nbr[i]), 1)), ('%s/v_%d/b' % (sc, i), (1,))]
+        return out
     n_s = n_s_ls[0]
     for i in range(N):
         s = '%s/%s_%d' % (sc, cell, i)
@@ -111,7 +146,16 @@ class OraclePolicy:
     def __init__(self, variant, n_s_ls, n_a, mask, n_h=64, n_fc=64, params=None,
                  dtype=torch.float32, n_env=1):
         assert variant in VARIANTS
-        self.variant, self.n_a, self.n_h, self.n_fc = variant, n_a, n_h, n_fc
+        self.hetero = is_hetero(n_a)
+        if self.hetero:
+            assert variant in SCOPE, 'heterogeneous agents exist for ma2c_nc / ma2c_ic3 / ma2c_dial only'
+            self.n_a_ls = [int(a) for a in n_a]
+            n_a_scalar = max(self.n_a_ls)
+        else:
+            n_a_scalar = int(n_a if np.isscalar(n_a) else n_a[0])
+            self.n_a_ls = [n_a_scalar] * len(mask)
+        self._n_a_arg = n_a
+        self.variant, self.n_a, self.n_h, self.n_fc = variant, n_a_scalar, n_h, n_fc
         self.mask = np.asarray(mask)
         self.N = len(self.mask)
         self.nbr = [list(np.where(self.mask[i] == 1)[0]) for i in range(self.N)]
@@ -173,12 +217,17 @@ class OraclePolicy:
                 hp = torch.relu(fp_in @ self._w(i, 'fcp/w') + self._w(i, 'fcp/b'))
                 s = torch.cat([hx, hp], dim=1)
                 wx, wh, b = self._w(i, 'lstm/wx'), self._w(i, 'lstm/wh'), self._w(i, 'lstm/b')
+            elif self.hetero and not nb:        # lstm_*_hetero, agent without neighbours: observation encoder only
+                wx, wh, b = self._w(i, 'wx_hid'), self._w(i, 'wh_hid'), self._w(i, 'b_hid')
+                act = torch.tanh if v == 'ma2c_ic3' else torch.relu
+                s = act(x[i][:, :self.n_s_ls[i]] @ self._w(i, 'w_ob') + self._w(i, 'b_ob'))
             else:
-                xi = torch.cat([x[i]] + [x[j] for j in nb], dim=1)
+                # hetero: every source contributes its own valid width (tf.slice(raw_xi, [j,0], [1, ns_dim]), :316-317)
+                xi = torch.cat([x[i][:, :self.n_s_ls[i]]] + [x[j][:, :self.n_s_ls[j]] for j in nb], dim=1)
                 wx, wh, b = self._w(i, 'wx_hid'), self._w(i, 'wh_hid'), self._w(i, 'b_hid')
                 if v == 'ma2c_nc':
                     mi = torch.cat([h[:, j] for j in nb], dim=1)
-                    pi_in = torch.cat([p[:, j] for j in nb], dim=1)
+                    pi_in = torch.cat([p[:, j, :self.n_a_ls[j]] for j in nb], dim=1)
                     hx = torch.relu(xi @ self._w(i, 'w_ob') + self._w(i, 'b_ob'))
                     hp = torch.relu(pi_in @ self._w(i, 'w_fp') + self._w(i, 'b_fp'))
                     hm = torch.relu(mi @ self._w(i, 'w_msg') + self._w(i, 'b_msg'))
@@ -202,13 +251,25 @@ class OraclePolicy:
     def _pi(self, i, h):
         return torch.softmax(h @ self._head(i, 'pi/w') + self._head(i, 'pi/b'), dim=-1)
 
+    def _pad_pi(self, pi):
+        """hetero: zero-pad to the widest action space so policies stack; padded entries carry probability 0."""
+        if pi.shape[-1] == self.n_a:
+            return pi
+        return torch.cat([pi, torch.zeros(*pi.shape[:-1], self.n_a - pi.shape[-1], dtype=pi.dtype)], dim=-1)
+
     def _v(self, i, h, actions):
         """actions [B,N] int64 (same-step actions); neighbours one-hot in ascending index."""
-        parts = [h] + [torch.nn.functional.one_hot(actions[:, j], self.n_a).to(self.dtype) for j in self.nbr[i]]
+        parts = [h] + [torch.nn.functional.one_hot(actions[:, j], self.n_a_ls[j]).to(self.dtype) for j in self.nbr[i]]
         return (torch.cat(parts, dim=1) @ self._head(i, 'v/w') + self._head(i, 'v/b')).squeeze(-1)
 
     def _prep(self, obs, ps):
         x = [torch.as_tensor(np.asarray(o), dtype=self.dtype).reshape(self.B, -1) for o in obs]
+        if ps is not None and self.hetero and not isinstance(ps, np.ndarray):      # list of per-agent [n_a_i] policies
+            pad = np.zeros((self.B, self.N, self.n_a))
+            for i, q in enumerate(ps):
+                q = np.asarray(q, dtype=np.float64).reshape(self.B, -1)
+                pad[:, i, :q.shape[1]] = q                                         # agents/models.py:229-235
+            ps = pad
         p = None if ps is None else torch.as_tensor(np.asarray(ps), dtype=self.dtype).reshape(self.B, self.N, self.n_a)
         return x, p
 
@@ -223,6 +284,8 @@ class OraclePolicy:
             c2, h2 = self._cell(x, p, d, c, h)
             if out_type.startswith('p'):
                 self.states_fw = torch.cat([c2, h2], dim=-1)
+                if self.hetero:                 # per-agent widths: a list like the reference's pi_ls (policies.py:296)
+                    return [self._pi(i, h2[:, i]).numpy() for i in range(self.N)]
                 return torch.stack([self._pi(i, h2[:, i]) for i in range(self.N)], dim=1).numpy()
             a = torch.as_tensor(np.asarray(actions), dtype=torch.int64).reshape(self.B, self.N)
             return torch.stack([self._v(i, h2[:, i], a) for i in range(self.N)], dim=1).numpy()
@@ -239,7 +302,7 @@ class OraclePolicy:
             d = torch.as_tensor(np.asarray(dones[t], dtype=np.float64).reshape(self.B), dtype=self.dtype)
             c, h = self._cell(x, p, d, c, h)
             a = torch.as_tensor(np.asarray(acts[t]), dtype=torch.int64).reshape(self.B, self.N)
-            pis.append(torch.stack([self._pi(i, h[:, i]) for i in range(self.N)], dim=1))
+            pis.append(torch.stack([self._pad_pi(self._pi(i, h[:, i])) for i in range(self.N)], dim=1))
             vs.append(torch.stack([self._v(i, h[:, i], a) for i in range(self.N)], dim=1))
         return torch.stack(pis), torch.stack(vs)
 
@@ -248,6 +311,11 @@ class OraclePolicy:
         a = torch.as_tensor(np.asarray(acts), dtype=torch.int64)
         R = torch.as_tensor(np.asarray(Rs), dtype=self.dtype)
         A = torch.as_tensor(np.asarray(Advs), dtype=self.dtype)
+        if self.hetero:
+            # Reference quirk Q7 (agents/policies.py:241-251): in the non-identical branch prob_pi is built as
+            # [N,1,T] and multiplied with ADV [N,T]; TF broadcasts that to [N,N,T], so after mean_t and the sum over
+            # everything agent i's log-probability is weighted by the SUM over agents of the advantages.
+            A = A.sum(dim=-1, keepdim=True).expand_as(A)
         log_pi = torch.log(torch.clamp(pi, 1e-10, 1.0))
         ent = -(pi * log_pi).sum(-1)                                  # [T,B,N]
         lp = torch.gather(log_pi, -1, a.unsqueeze(-1)).squeeze(-1)

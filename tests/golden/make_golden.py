@@ -333,6 +333,87 @@ def tfnet_case(ini, total_step):
     return out
 
 
+# ---- heterogeneous agents: lstm_comm_hetero / lstm_ic3_hetero / lstm_dial_hetero ---------------------
+HETERO = dict(edges=[(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (1, 4)],
+              n_s_ls=[5, 7, 4, 6, 5, 3], n_a_ls=[4, 3, 5, 2, 4, 3], n_step=8, updates=3)
+
+
+def hetero_case(agent):
+    """The UNMODIFIED reference agent / policy / layer code for agents with UNEQUAL observation and action widths
+    (agents/utils.py:220-341, 420-512, 602-702; agents/models.py:89-97, 229-235; agents/policies.py:289, 453, 502)
+    on the TF shim.  CACC agents are identical, so a scripted stream stands in for the environment: random
+    observations, rewards and action uniforms from a fixed RandomState; everything the policy returns is recorded."""
+    import importlib
+    sys.setrecursionlimit(100000)
+    sys.path.insert(0, HERE)
+    tf = importlib.import_module('tf_shim')
+    sys.modules['tensorflow'] = tf
+    for mod in ('agents.models', 'agents.policies', 'agents.utils', 'utils', 'envs.cacc_env'):
+        sys.modules.pop(mod, None)
+    import agents.models as am
+    H = HETERO
+    N = len(H['n_s_ls'])
+    mask = np.zeros((N, N), dtype=int)
+    for a, b in H['edges']:
+        mask[a, b] = mask[b, a] = 1
+    dist = np.zeros((N, N), dtype=int)
+    cp = _cfg('config_ma2c_nc_catchup.ini')
+    mc = cp['MODEL_CONFIG']
+    mc['batch_size'] = str(H['n_step'])
+    cls = {'ma2c_nc': am.MA2C_NC, 'ma2c_ic3': am.MA2C_IC3, 'ma2c_dial': am.MA2C_DIAL}[agent]
+    np.random.seed(12)
+    model = cls(H['n_s_ls'], H['n_a_ls'], mask, dist, -1.0, 10 ** 6, mc, seed=12)
+    assert not model.identical_agent
+    w0 = tf.variable_values()
+    rs = np.random.RandomState(3)
+    T = H['n_step']
+    log, obs_l, uni_l, rew_l = [], [], [], []
+    fp = [np.ones(n) / n for n in H['n_a_ls']]
+    done = True
+    model.reset()
+
+    def decide(ob, done, fp):
+        pi = model.forward(ob, done, fp)
+        pi = [np.asarray(p, dtype=np.float64).ravel() for p in pi]
+        log.append(np.concatenate(pi))
+        u = rs.rand(N)
+        uni_l.append(u)
+        act = []
+        for i in range(N):
+            cdf = np.cumsum(pi[i]); cdf = cdf / cdf[-1]
+            act.append(int(np.searchsorted(cdf, u[i], side='right')))
+        return pi, np.array(act)
+    for upd in range(H['updates']):
+        for t in range(T):
+            ob = [rs.randn(n) for n in H['n_s_ls']]
+            obs_l.append(np.concatenate(ob))
+            pi, act = decide(ob, done, fp)
+            v = model.forward(ob, done, fp, act, 'v')
+            log.append(np.asarray(v, dtype=np.float64).ravel())
+            r = float(rs.randn() * 300.0)
+            rew_l.append(r)
+            model.add_transition(ob, fp, act, r, v, False)
+            fp = [np.asarray(p, dtype=np.float32) for p in pi]
+            done = False
+        ob = [rs.randn(n) for n in H['n_s_ls']]
+        obs_l.append(np.concatenate(ob))
+        pi, act = decide(ob, done, fp)
+        R = model.forward(ob, done, fp, act, 'v')
+        log.append(np.asarray(R, dtype=np.float64).ravel())
+        model.backward(R, 0)
+        # the reference Trainer re-feeds the boundary observation as the first one of the next batch; the scripted
+        # stream simply continues with fresh observations (the LSTM state keeps running, states_bw := states_fw)
+    w1 = tf.variable_values()
+    out = dict(trace=np.concatenate(log), obs=np.concatenate(obs_l), uniforms=np.array(uni_l), rewards=np.array(rew_l),
+               names=np.array(list(w0)), mask=mask, n_s_ls=np.array(H['n_s_ls']), n_a_ls=np.array(H['n_a_ls']),
+               n_step=T, updates=H['updates'])
+    for n in w0:
+        out['w0sha/' + n] = hashlib.sha256(np.ascontiguousarray(w0[n]).tobytes()).hexdigest()
+        out['w0shape/' + n] = np.array(w0[n].shape)
+        out['w1/' + n] = w1[n]
+    return out
+
+
 def scheduler_case(au):
     s1 = au.Scheduler(5e-4, decay='constant')
     s2 = au.Scheduler(5e-4, 1e-4, 1e6, decay='linear')
@@ -400,6 +481,13 @@ def main():
         out = agent_case(CACCEnv, ini, total)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
         print(name, 'trace', out['trace'].shape, 'data', out['data'].tolist(), 'seed', out['seed_after'], 'steps', out['cur_step'])
+    for agent in ('ma2c_nc', 'ma2c_ic3', 'ma2c_dial'):
+        name = 'hetero_' + agent
+        if os.path.exists(os.path.join(HERE, name + '.npz')) and '--force' not in sys.argv:
+            continue
+        out = hetero_case(agent)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, 'trace', out['trace'].shape, 'n_var', len(out['names']))
     if '--force' not in sys.argv:
         return
     for name, alpha, multi in [('buffer_ma_global', -1, True), ('buffer_ma_spatial09', 0.9, True),
