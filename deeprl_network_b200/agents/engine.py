@@ -339,8 +339,9 @@ class PolicyEngine:
         self.sv_gates = z(T, N, B, 4 * NH)
         self.sv_enc = z(T, N, B, 128) if self.variant in ('ma2c_ic3', 'ma2c_dial') else None
         self.sv_dlv = z(T, N, B, 8)
-        self.sv_dz = z(T, N, B, 4 * NH)
-        self.sv_dpre = z(T, N, B, 192)
+        # tensor-core path: sv_dz holds per-tile gate-bias partial sums, sv_dpre is unused (operand tiles instead)
+        self.sv_dz = z(T, N, B // 128, 4 * NH) if self.use_tc else z(T, N, B, 4 * NH)
+        self.sv_dpre = z(4) if self.use_tc else z(T, N, B, 192)
         # tensor-core path: dz / encoder pre-activation gradients additionally as K-major [hi | lo] operand tiles
         ndp = {'ma2c_nc': 192, 'ia2c': 64}.get(self.variant, 128)
         self.sv_dzT = z(T, N, B // 32, 2 * 256 * 32) if self.use_tc else None

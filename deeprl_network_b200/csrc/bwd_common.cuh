@@ -18,7 +18,7 @@ struct BwdK {
   const float* c_prev; const float* c_cur;      // c_seq[t], c_seq[t+1]
   const float* dh_in; const float* dc_in; const float* dmsg_in;       // produced by step t+1
   float* dh_out; float* dc_out; float* dmsg_out;                       // consumed by step t-1
-  float* sv_dz; float* sv_dpre;                                        // step t
+  float* sv_dz; float* sv_dpre;                                        // step t (tcgen05 path: sv_dz = [N][tiles][256] gate-bias partials)
   const float* wpack; int* tc_err;                                     // tcgen05 path (NULL -> FFMA)
   float* dzT;                                                          // step t: [N][B/32][hi|lo][256][32] tiles or NULL
   float* dpT;                                                          // step t: [N][B/32][hi|lo][ndp][32] tiles (encoder pre-act grads)
@@ -34,4 +34,5 @@ int nmarl_tc_ndp(const nmarl_model* m);
 // all GEMM weight gradients (gate + encoders) of the tensor-core path; activations are feature-major
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
                            const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st, cudaStream_t st_bias,
-                           bool raw_tiles = false, void** ev_wgrad = nullptr);
+                           bool raw_tiles = false, void** ev_wgrad = nullptr,
+                           const float* h_seq = nullptr, const float* done_pre = nullptr);

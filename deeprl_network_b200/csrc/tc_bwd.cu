@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   int* n_kb_s = reinterpret_cast<int*>(tmem_slot + 1);
   KbEnt* sched = reinterpret_cast<KbEnt*>(tmem_slot + 4);
+  float* bsum = reinterpret_cast<float*>(sched + MAX_KB);         // [4 quarters][256] gate-bias partial sums
 
   const int i = blockIdx.y;
   const nmarl_agent& ag = m.agent[i];
@@ -68,7 +69,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
     const float* gates_fm = k.sv_gates + (size_t)i * NG * B;
     const float* sh_fm = k.sv_sh + (size_t)i * (SD + NH) * B;
     const float* enc_fm = k.sv_enc ? k.sv_enc + (size_t)i * 128 * B : nullptr;
-    float* dz_fm = k.sv_dz + (size_t)i * NG * B;
 
     // ---- total dh and dc for the thread's units --------------------------------------------------------------
     float dh[EW], dct[EW];
@@ -143,7 +143,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           dz[j] = dh[j] * tcv * go[j] * (1.0f - go[j]);
         }
       }
-      st_fm<EW>(dz_fm, g * NH + e0, B, b, dz);              // feature-major copy for the gate-bias column sums
+      {   // gate-bias gradient = column sums of dz: sum over this warp's 32 rows by recursive halving (16 shuffles per
+          // gate instead of a feature-major copy of dz in HBM + a separate column-sum kernel)
+        float a[EW];
+#pragma unroll
+        for (int j = 0; j < EW; ++j) a[j] = dz[j];
+#pragma unroll
+        for (int half = EW / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+          const bool up = (lane & bit) != 0;
+#pragma unroll
+          for (int j = 0; j < half; ++j) {
+            const float send = up ? a[j] : a[j + half];
+            const float keep = up ? a[j + half] : a[j];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+        a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+        const int col = (((lane >> 4) & 1) << 3) | (((lane >> 3) & 1) << 2) | (((lane >> 2) & 1) << 1) | ((lane >> 1) & 1);
+        if ((lane & 1) == 0) bsum[quarter * NG + g * NH + e0 + col] = a[0];
+      }
       if (k.dzT != nullptr) {                 // dz^T tile for the tensor-core wgrad: K-major over rows, hi | lo
         uint8_t* tile = reinterpret_cast<uint8_t*>(k.dzT) + ((size_t)i * (B / 32) + (b0 / 32) + quarter) * (size_t)((RAW ? 1 : 2) * 256 * 128);
 #pragma unroll
@@ -161,6 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
     }
 
+    // per-tile gate-bias partial sums (fixed order over the four row quarters), reduced over (t, tile) afterwards
+    row_barrier();
+    if (tid < NG) {
+      const float sm = ((bsum[tid] + bsum[NG + tid]) + bsum[2 * NG + tid]) + bsum[3 * NG + tid];
+      k.sv_dz[((size_t)i * gridDim.x + blockIdx.x) * NG + tid] = sm;
+    }
     // ---- dgrad result: d[s | h^] -------------------------------------------------------------------------------
     tc::mbar_wait(acc_full, 0, k.tc_err, 13);
     tc::fence_after_sync();

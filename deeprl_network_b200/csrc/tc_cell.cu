@@ -197,11 +197,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           } else {
             ld_state<FM, W>(src, (size_t)ag.nbr[s], b, hb * 32 + c0, B, t);
           }
-          if (SAVE) st_fm<W>(xin_fm, xm0 + s * NH + hb * 32 + c0, B, b, t);
+          // NeurComm with feature-major state: m~ is a plain copy of the neighbours' h_seq[t]; the weight-gradient
+          // kernel reads it from there (tc_wgrad.cu), so it is not saved a second time
+          if (SAVE && !(FM && VAR == NMARL_NC)) st_fm<W>(xin_fm, xm0 + s * NH + hb * 32 + c0, B, b, t);
           produce_in(c, t);
         }
       }
-      if (SAVE) {
+      if (SAVE && !(FM && VAR == NMARL_NC)) {
         float z[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) z[j] = 0.f;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     }
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-      if (SAVE) st_fm<W>(sh_fm, SD + hb * 32 + c0, B, b, hv[hb]);
+      if (SAVE && !FM) st_fm<W>(sh_fm, SD + hb * 32 + c0, B, b, hv[hb]);   // FM: h^ = (1 - done) * h_seq[t], re-derived by tc_wgrad
       produce_in(c, hv[hb]);
     }
     STAMP();

@@ -20,6 +20,7 @@ enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_M0, J_ENC_M1, J_COUNT };
 struct TcWgK {
   int B, T, splits, ndp;
   const float* sv_sh; const float* sv_xin; const float* dzT; const float* dpT;
+  const float* h_seq; const float* done_pre;   // feature-major state path: h^ / m~ operand rows come from the state sequence
   float* ws;
   long long ws_off[J_COUNT];     // float offset of each job's partial block [splits][N_agents][128][N_job]
   int jobs[J_COUNT]; int n_jobs; // job kinds present
@@ -116,10 +117,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     const bool is_p = ka > d.ka_cnt && ka <= d.ka_cnt + d.p_cnt;
     const bool real = ka < d.ka_cnt || is_p;
     const int feat = is_p ? d.p_feat0 + (ka - d.ka_cnt - 1) : d.a_feat0 + ka;
+    // Feature-major state path: the forward kernel does not save h^ (= (1 - done) * own h_seq[t]) and, for NeurComm,
+    // m~ (= the neighbours' h_seq[t]) a second time; those operand rows are read from the state sequence itself.
+    int hs_agent = -1, hs_unit = 0;
+    bool hs_mask = false;
+    if (k.h_seq != nullptr && real && !is_p) {
+      if ((kind == J_GATE0 || kind == J_GATE1) && feat >= m.s_dim) { hs_agent = i; hs_unit = feat - m.s_dim; hs_mask = true; }
+      else if ((kind == J_ENC_M0 || kind == J_ENC_M1) && m.variant == NMARL_NC) {
+        const int fm = feat - (m.kx_pad + m.kp_pad);
+        hs_agent = m.agent[i].nbr[fm / NH]; hs_unit = fm % NH;
+      }
+    }
     for (int q = 0; q < nkb; ++q) {
       const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
       float x[W];
-      if (real) {
+      if (hs_agent >= 0) {
+        const float* src = k.h_seq + (((size_t)t * N_agents + hs_agent) * NH + hs_unit) * k.B + rb * 32 + set * W;
+#pragma unroll
+        for (int p = 0; p < W / 4; ++p) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * p));
+          x[4 * p] = v.x; x[4 * p + 1] = v.y; x[4 * p + 2] = v.z; x[4 * p + 3] = v.w;
+        }
+        if (hs_mask) {
+          const float* dn = k.done_pre + (size_t)t * k.B + rb * 32 + set * W;
+#pragma unroll
+          for (int p = 0; p < W / 4; ++p) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dn + 4 * p));
+            x[4 * p] *= 1.0f - v.x; x[4 * p + 1] *= 1.0f - v.y; x[4 * p + 2] *= 1.0f - v.z; x[4 * p + 3] *= 1.0f - v.w;
+          }
+        }
+      } else if (real) {
         const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * W;
 #pragma unroll
         for (int p = 0; p < W / 4; ++p) {
@@ -248,23 +275,24 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
   }
 }
 
-// gate bias gradient: column sums of the feature-major dz (one CTA per (agent, gate column); coalesced)
-__global__ void __launch_bounds__(256) dz_colsum_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ dz,
-                                                       int B, int T, float* __restrict__ grads) {
-  __shared__ float red[8];
-  const int n = blockIdx.x, i = blockIdx.y;
+// gate bias gradient: fixed-order reduce of the per-tile partial sums the backward cell kernel left in sv_dz
+// ([t][agent][tile][256]); one CTA per (32 columns, agent), 8 strided partial chains per column + an ordered tail
+__global__ void __launch_bounds__(256) gate_bias_reduce_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ part,
+                                                              int tiles, int T, float* __restrict__ grads) {
+  __shared__ float red[8][32];
+  const int c = threadIdx.x & 31, p = threadIdx.x >> 5, col = blockIdx.x * 32 + c, i = blockIdx.y;
+  const int n = T * tiles;
   float s = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float* p = dz + (((size_t)t * m.n_agent + i) * NG + n) * B;
-    for (int b = threadIdx.x; b < B; b += 256) s += __ldcs(p + b);
+  for (int e = p; e < n; e += 8) {
+    const int t = e / tiles, tile = e - t * tiles;
+    s += part[(((size_t)t * m.n_agent + i) * tiles + tile) * NG + col];
   }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  red[p][c] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (p == 0) {
     float tsum = 0.f;
-    for (int w = 0; w < 8; ++w) tsum += red[w];
-    grads[m.agent[i].o_b + n] = tsum;
+    for (int w = 0; w < 8; ++w) tsum += red[w][c];
+    grads[m.agent[i].o_b + col] = tsum;
   }
 }
 
@@ -306,10 +334,11 @@ int64_t nmarl_tc_wgrad_ws_floats(const nmarl_model* m) {
 
 int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_sh, const float* sv_xin, const float* dzT,
                            const float* dpT, const float* sv_dz, float* ws, float* grads, int* err, cudaStream_t st,
-                           cudaStream_t st_bias, bool raw_tiles, void** ev_wgrad) {
+                           cudaStream_t st_bias, bool raw_tiles, void** ev_wgrad, const float* h_seq, const float* done_pre) {
   TcWgK k{};
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
+  k.h_seq = h_seq; k.done_pre = done_pre;
   k.n_jobs = job_list(m, k.jobs);
   long long off = 0;
   for (int j = 0; j < k.n_jobs; ++j) { k.ws_off[j] = off; off += (long long)k.splits * m->n_agent * 128 * job_N(m, k.jobs[j]); }
@@ -319,7 +348,7 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
     NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
-  dz_colsum_kernel<<<dim3(NG, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B, T, grads);   // independent of the GEMM jobs
+  gate_bias_reduce_kernel<<<dim3(NG / 32, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B / 128, T, grads);   // independent of the GEMM jobs
   NMARL_LAUNCH_CHECK();
   if (ev_wgrad) NMARL_CUDA(cudaEventRecord((cudaEvent_t)ev_wgrad[0], st));
   if (raw_tiles) tc_wgrad_kernel<true><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);

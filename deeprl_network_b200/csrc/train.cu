@@ -912,11 +912,12 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
       k.dmsg_in = a->dmsg + (size_t)pin * nb * NMARL_MAX_NBR * NH;
       k.dmsg_out = a->dmsg + (size_t)pout * nb * NMARL_MAX_NBR * NH;
     }
-    k.sv_dz = a->sv_dz + (size_t)t * nb * NG;
     k.sv_dpre = a->sv_dpre + (size_t)t * nb * 192;
     k.wpack = a->wpack; k.tc_err = a->tc_err; k.state_fm = a->state_fm;
     k.raw_tiles = raw_tiles;
     const bool use_tc = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
+    // tensor-core path: sv_dz holds the per-tile gate-bias partial sums [T][N][B/128][256]; FFMA path: dz [T][N][B][256]
+    k.sv_dz = use_tc ? a->sv_dz + (size_t)t * N * (B / 128) * NG : a->sv_dz + (size_t)t * nb * NG;
     k.dzT = (use_tc && a->sv_dzT) ? a->sv_dzT + (size_t)t * N * (B / 32) * (2 * 256 * 32) : nullptr;
     k.ndp = nmarl_tc_ndp(m);
     k.dpT = (use_tc && a->sv_dpT) ? a->sv_dpT + (size_t)t * N * (B / 32) * (2 * k.ndp * 32) : nullptr;
@@ -951,7 +952,8 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     // the gate-bias column sums only read sv_dz: second fork, beside the GEMM jobs
     NMARL_CUDA(cudaEventRecord(ev_fork, st));
     NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side, raw_tiles != 0, a->ev_wgrad)) return 1;
+    if (nmarl_tc_launch_wgrads(m, B, T, a->sv_sh, a->sv_xin, a->sv_dzT, a->sv_dpT, a->sv_dz, a->ws, a->grads, a->tc_err, st, side, raw_tiles != 0, a->ev_wgrad,
+                               a->state_fm ? a->h_seq : nullptr, a->done_pre)) return 1;
     NMARL_CUDA(cudaEventRecord(ev_join, side));
     NMARL_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     NMARL_DBG_SYNC(st, "tc_wgrads");

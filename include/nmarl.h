@@ -188,6 +188,7 @@ int nmarl_nstep_return_adv(int n_agent, int B, int T, int NR, const double* rewa
  *   sv_xin [T][N][B][kx_pad+kp_pad+km_pad]  sv_sh [T][N][B][s_dim+64]  sv_gates [T][N][B][256]
  *   sv_enc [T][N][B][128] (IC3: 64 used; DIAL: 128)   sv_dlv [T][N][B][8]
  *   sv_dz [T][N][B][256]   sv_dpre [T][N][B][192]   sv_dmp [T][N][B][64] (DIAL)
+ *   (tensor-core path: sv_dz = [T][N][B/128][256] per-tile gate-bias partial sums, sv_dpre unused)
  *   dh_rec, dc_rec [2][N][B][64]   dmsg [2][N][MAX_NBR][B][64]
  *   wt [n_wt] transposed weights   ws: split-K workspace of ws_floats floats
  *   loss_part float [T][N][tiles][4] per-CTA partial sums (policy, value, entropy, pad)
@@ -212,8 +213,10 @@ typedef struct {
   float* sv_dzT;             /* tensor-core path: dz^T as [T][N][B/32][hi|lo][256][32] swizzled tiles  */
   float* sv_dpT;             /* tensor-core path: encoder pre-activation grads^T, [T][N][B/32][hi|lo][ndp][32],
                                 ndp = 192 (NC) / 128 (IC3, DIAL) / 64 (IA2C).  On the tensor-core path (wpack set,
-                                B % 128 == 0) sv_xin / sv_sh / sv_gates / sv_enc / sv_dz are FEATURE-MAJOR
-                                [T][N][feature][B] and sv_dpre is unused.                                          */
+                                B % 128 == 0) sv_xin / sv_sh / sv_gates / sv_enc are FEATURE-MAJOR
+                                [T][N][feature][B] and sv_dpre is unused.  With state_fm the done-masked own state
+                                (rows s_dim.. of sv_sh) and, for NeurComm, the neighbour messages (the m~ block of
+                                sv_xin) are NOT stored a second time: the weight-gradient kernel reads h_seq.        */
   int32_t state_fm;          /* tensor-core path only: h_seq / c_seq / msg_seq / dh_rec / dc_rec / dmsg are
                                 feature-major ([..][64][B] instead of [..][B][64])                                  */
   nmarl_ctx* ctx;            /* required by nmarl_a2c_bptt / nmarl_a2c_backward (forked side work)                  */
