@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           if constexpr (RAW) {
             __stcs(reinterpret_cast<float*>(tile + off), dz[j]);
           } else {
-            const float hi = __uint_as_float(__float_as_uint(dz[j]) & 0xFFFFE000u);
+            float hi, lo;
+            tc::split_tf32(dz[j], hi, lo);
             __stcs(reinterpret_cast<float*>(tile + off), hi);                       // read once, by the wgrad kernel
-            __stcs(reinterpret_cast<float*>(tile + 256 * 128 + off), dz[j] - hi);
+            __stcs(reinterpret_cast<float*>(tile + 256 * 128 + off), lo);
           }
         }
       }
@@ -201,9 +202,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
         if constexpr (RAW) {
           __stcs(reinterpret_cast<float*>(dptile + off), vals[j]);
         } else {
-          const float hi = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
+          float hi, lo;
+          tc::split_tf32(vals[j], hi, lo);
           __stcs(reinterpret_cast<float*>(dptile + off), hi);
-          __stcs(reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off), vals[j] - hi);
+          __stcs(reinterpret_cast<float*>(dptile + (size_t)k.ndp * 128 + off), lo);
         }
       }
     };

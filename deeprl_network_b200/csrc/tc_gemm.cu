@@ -17,8 +17,8 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int ldw, int K, int n
     const int kb = idx / (nrows * 32);
     const int k = kb * 32 + kk;
     const float x = (k < K) ? W[(size_t)k * ldw + n0 + n] : 0.f;
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    const float lo = x - hi;
+    float hi, lo;
+    tc::split_tf32(x, hi, lo);
     char* tile = reinterpret_cast<char*>(out) + (size_t)kb * 2 * nrows * 128;
     const uint32_t off = tc::sw128_offset(n, kk);
     *reinterpret_cast<float*>(tile + off) = hi;
@@ -37,11 +37,10 @@ __global__ void pack_b_raw_kernel(const float* __restrict__ W, int ldw, int K, i
     const int n = idx % nrows, kk = (idx / nrows) % 32, kb = idx / (nrows * 32);
     const int k = kb * 32 + kk;
     const float x = (k < K) ? W[(size_t)k * ldw + n0 + n] : 0.f;
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     char* tile = reinterpret_cast<char*>(out) + (size_t)kb * 2 * nrows * 128;
     const uint32_t off = tc::sw128_offset(n, kk);
     *reinterpret_cast<float*>(tile + off) = x;
-    *reinterpret_cast<float*>(tile + (size_t)nrows * 128 + off) = x - hi;
+    *reinterpret_cast<float*>(tile + (size_t)nrows * 128 + off) = tc::tf32_lo_of_raw(x);
   }
 }
 
@@ -189,10 +188,8 @@ __global__ void __launch_bounds__(192, 1) tc_gemm_ss_test_kernel(const float* __
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < K) v = *reinterpret_cast<const float4*>(A + row * K + k);
         float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y);
+        tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
         const uint32_t off = tc::sw128_offset((uint32_t)tid, (uint32_t)(q * 4));
         *reinterpret_cast<float4*>(hi_t + off) = h;
         *reinterpret_cast<float4*>(lo_t + off) = l;

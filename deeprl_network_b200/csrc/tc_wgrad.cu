@@ -166,10 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         for (uint32_t e = (uint32_t)tid; e < tile_bytes / 16; e += ROW_THREADS) {
           const float4 v = raw[e];
           float4 l;
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = tc::tf32_lo_of_raw(v.x); l.y = tc::tf32_lo_of_raw(v.y);
+          l.z = tc::tf32_lo_of_raw(v.z); l.w = tc::tf32_lo_of_raw(v.w);
           lo[e] = l;
         }
         tc::fence_proxy_async();

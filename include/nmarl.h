@@ -155,7 +155,7 @@ typedef struct {
 int nmarl_policy_step_p(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
 int nmarl_policy_step_v(const nmarl_model* m, const nmarl_fwd_args* a, void* stream);
 /* Pack the GEMM weights for the tcgen05 path: per 32-wide k-block a [hi | lo] pair of 128B-swizzled
- * K-major tiles of W^T (hi = value truncated to TF32, lo = remainder).  Call after every parameter
+ * K-major tiles of W^T (hi = value rounded to TF32, lo = rounded remainder).  Call after every parameter
  * change.  wt (transposed weights scratch, n_wt floats) is also refreshed.                           */
 int nmarl_pack_weights(const nmarl_model* m, const float* params, float* wt, float* wpack, void* stream);
 /* DIAL only: msg[N][B][64] = relu(h W_mfc + b) (agents/utils.py:563-566); needed after a reset */
