@@ -99,7 +99,7 @@ class PolicyEngine:
         self.T_cur = T
         self.launches = 0
         # single-copy operand tiles for the weight-gradient GEMMs (nmarl_bwd_args.raw_tiles)
-        self.raw_tiles = self.use_tc and os.environ.get('NMARL_RAW_TILES', '0') == '1'
+        self.raw_tiles = self.use_tc and os.environ.get('NMARL_RAW_TILES', '1') != '0'
         self.bwd_events = None             # bench.py: (step events [2T], wgrad events [2]) recorded inside nmarl_a2c_bptt
         self._ctx = C.c_void_p()
         L.check(L.lib().nmarl_create(C.byref(self._ctx)), 'nmarl_create')

@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         hs_agent = m.agent[i].nbr[fm / NH]; hs_unit = fm % NH;
       }
     }
-    for (int q = 0; q < nkb; ++q) {
+    // the A operand of k-block q: 8 consecutive envs of this thread's feature (global loads; issued one k-block AHEAD so
+    // that their latency hides behind the lo pass / the barrier waits of the current k-block)
+    auto load_x = [&](int q, float (&x)[W]) {
       const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
-      float x[W];
       if (hs_agent >= 0) {
         const float* src = k.h_seq + (((size_t)t * N_agents + hs_agent) * NH + hs_unit) * k.B + rb * 32 + set * W;
 #pragma unroll
@@ -157,6 +158,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < W; ++j) x[j] = one ? 1.0f : 0.0f;
       }
+    };
+    float xn[W];
+    if (nkb > 0) load_x(0, xn);
+    for (int q = 0; q < nkb; ++q) {
+      float x[W];
+#pragma unroll
+      for (int j = 0; j < W; ++j) x[j] = xn[j];
+      if (q + 1 < nkb) load_x(q + 1, xn);
       produce_in(c, x);
       if constexpr (RAW) {                                              // lo half of this k-block's B stage
         const int st = q % S_STAGES;

@@ -14,9 +14,19 @@ pi = torch.zeros(8, B, 4, device='cuda'); act = torch.zeros(8, B, dtype=torch.in
 for it in range(3):
     eng.step_p(obs, fp, done, pi, act, L.SAMPLE_PHILOX)
 lib.nmarl_debug_set_prof.argtypes = [C.c_void_p]
-lib.nmarl_debug_set_prof(prof.data_ptr())
-eng.step_p(obs, fp, done, pi, act, L.SAMPLE_PHILOX)
+mode = sys.argv[1] if len(sys.argv) > 1 else 'p'
+if mode == 'ps':                       # rollout p-call that also saves the BPTT activations
+    eng._alloc_train()
+    eng.h_seq[0].copy_(eng.h[eng.cur]); eng.c_seq[0].copy_(eng.c[eng.cur])
+    for it in range(2):
+        eng._seq_call(0, obs, fp, done, 'p', pi=pi, action=act, mode=L.SAMPLE_PHILOX, save=True)
+    lib.nmarl_debug_set_prof(prof.data_ptr())
+    eng._seq_call(0, obs, fp, done, 'p', pi=pi, action=act, mode=L.SAMPLE_PHILOX, save=True)
+else:
+    lib.nmarl_debug_set_prof(prof.data_ptr())
+    eng.step_p(obs, fp, done, pi, act, L.SAMPLE_PHILOX)
 torch.cuda.synchronize()
+print('mode', mode)
 p = prof.cpu().numpy()
 n = int(p[31])
 names = ['start', 'inputs loaded', 'enc A produced', 'enc ready', 'all A produced', 'acc ready', 'it0 tmem loaded', 'it0 math done',
