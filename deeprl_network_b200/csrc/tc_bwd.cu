@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       tc::fence_before_sync();
     }
   } else if (warp == ROW_THREADS / 32) {
-    if (lane == 0) producer_loop(sched, n_kb, bst, b_full, b_empty, k.wpack, k.tc_err);
+    if (tc::elect_one()) producer_loop(sched, n_kb, bst, b_full, b_empty, k.wpack, k.tc_err);
   } else {
-    if (lane == 0) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, k.tc_err);
+    if (tc::elect_one()) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, k.tc_err);
   }
   __syncthreads();
   if (warp == ROW_THREADS / 32 + 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem, 512); }

@@ -459,10 +459,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     }
   } else if (warp == ROW_THREADS / 32) {
     // =================================== B producer ======================================================
-    if (lane == 0) producer_loop(sched, n_kb, bst, b_full, b_empty, a.wpack, a.tc_err);
+    if (tc::elect_one()) producer_loop(sched, n_kb, bst, b_full, b_empty, a.wpack, a.tc_err);
   } else {
     // =================================== MMA issuer ======================================================
-    if (lane == 0) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, a.tc_err,
+    if (tc::elect_one()) mma_loop(sched, n_kb, bst, b_full, b_empty, a_full, a_empty, enc_full, acc_full, tmem, a.tc_err,
                             (k.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1) ? k.prof : nullptr);
   }
   __syncthreads();
