@@ -69,7 +69,7 @@ class BwdArgs(C.Structure):
                 ('wt', C.c_void_p), ('ws', C.c_void_p), ('ws_floats', C.c_int64),
                 ('loss_part', C.c_void_p), ('grads', C.c_void_p), ('wpack', C.c_void_p), ('tc_err', C.c_void_p),
                 ('sv_dzT', C.c_void_p), ('sv_dpT', C.c_void_p), ('state_fm', C.c_int32),
-                ('ctx', C.c_void_p), ('raw_tiles', C.c_int32), ('ev_step', C.c_void_p), ('ev_wgrad', C.c_void_p)]
+                ('ctx', C.c_void_p), ('raw_tiles', C.c_int32), ('ev_step', C.c_void_p), ('ev_wgrad', C.c_void_p), ('fused_heads', C.c_int32)]
 
 
 _lib = None

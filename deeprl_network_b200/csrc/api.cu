@@ -33,11 +33,12 @@ extern "C" int nmarl_create(nmarl_ctx** out) {
   NMARL_CHECK(out != nullptr, "nmarl_create: out is NULL");
   nmarl_ctx* c = new (std::nothrow) nmarl_ctx();
   NMARL_CHECK(c != nullptr, "nmarl_create: out of host memory");
-  c->side = nullptr; c->fork = nullptr; c->join = nullptr;
+  c->side = nullptr; c->fork = nullptr; c->join = nullptr; c->heads = nullptr;
   cudaError_t e = cudaGetDevice(&c->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->heads, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     nmarl_set_error("nmarl_create: %s", cudaGetErrorString(e));
     nmarl_destroy(c);
@@ -51,6 +52,7 @@ extern "C" int nmarl_destroy(nmarl_ctx* c) {
   if (c == nullptr) return 0;
   if (c->fork) cudaEventDestroy(c->fork);
   if (c->join) cudaEventDestroy(c->join);
+  if (c->heads) cudaEventDestroy(c->heads);
   if (c->side) cudaStreamDestroy(c->side);
   delete c;
   return 0;

@@ -6,7 +6,7 @@
 // the opaque context of the C ABI: helper stream + events for forked side work (created on the current device)
 struct nmarl_ctx {
   cudaStream_t side;
-  cudaEvent_t fork, join;
+  cudaEvent_t fork, join, heads;
   int device;
 };
 

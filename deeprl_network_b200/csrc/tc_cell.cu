@@ -543,30 +543,71 @@ __global__ void tc_transpose_kernel(const float* __restrict__ src, float* __rest
 }
 }  // namespace
 
+namespace {
+// One launch packs every tensor-core operand of every agent: per 32-deep k-block a [hi | lo] pair of 128B-swizzled
+// K-major tiles (see tc.cuh).  Job j of agent i (blockIdx.y = i * PACK_JOBS + j) is one matrix; the backward
+// operands (transposed weights) are gathered straight from the parameters with transposed indexing, so no
+// transposed copy is needed on this path.
+enum { PJ_X = 0, PJ_P, PJ_M, PJ_G, PJ_GT, PJ_MT, PJ_MFC, PJ_MFCT, PACK_JOBS };
+struct PackJob { int src, ld, K, N, transposed, dst; };     // operand element (k, n) = transposed ? W[n * ld + k] : W[k * ld + n]
+
+__device__ __forceinline__ PackJob pack_job(const nmarl_model& m, int i, int j) {
+  const nmarl_agent& ag = m.agent[i];
+  const int SD = m.s_dim, Kx = ag.x_nsrc * ag.x_w;
+  const int Km = (m.variant == NMARL_IC3) ? NH : ag.n_nbr * NH;
+  PackJob p{0, 0, 0, 0, 0, -1};
+  switch (j) {
+    case PJ_X: p = PackJob{ag.o_w_ob, NH, Kx, NH, 0, ag.tp_x}; break;
+    case PJ_P: if (m.variant == NMARL_NC) p = PackJob{ag.o_w_fp, NH, ag.n_nbr * m.n_a, NH, 0, ag.tp_p}; break;
+    case PJ_M: if (m.variant != NMARL_IA2C && Km > 0) p = PackJob{ag.o_w_msg, NH, Km, NH, 0, ag.tp_m}; break;
+    case PJ_G: p = PackJob{ag.o_wxh, NG, SD + NH, NG, 0, ag.tp_g}; break;
+    case PJ_GT: p = PackJob{ag.o_wxh, NG, NG, SD + NH, 1, ag.tp_gT}; break;
+    case PJ_MT: if (m.variant != NMARL_IA2C && Km > 0) p = PackJob{ag.o_w_msg, NH, NH, Km, 1, ag.tp_mT}; break;
+    case PJ_MFC: if (m.variant == NMARL_DIAL) p = PackJob{ag.o_mfc_w, NH, NH, NH, 0, ag.tp_mfc}; break;
+    case PJ_MFCT: if (m.variant == NMARL_DIAL) p = PackJob{ag.o_mfc_w, NH, NH, NH, 1, ag.tp_mfcT}; break;
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ nmarl_model m, const float* __restrict__ params,
+                                                       float* __restrict__ wpack) {
+  const int i = blockIdx.y / PACK_JOBS, j = blockIdx.y % PACK_JOBS;
+  const PackJob p = pack_job(m, i, j);
+  if (p.dst < 0 || p.K <= 0 || p.N <= 0) return;
+  const float* W = params + p.src;
+  const int nkb = (p.K + 31) / 32;
+  const int total = nkb * p.N * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int n, kk, kb;
+    if (p.transposed) { kk = idx & 31; n = (idx >> 5) % p.N; kb = idx / (32 * p.N); }      // consecutive threads -> consecutive k
+    else { n = idx % p.N; kk = (idx / p.N) & 31; kb = idx / (p.N * 32); }                  // consecutive threads -> consecutive n
+    const int k = kb * 32 + kk;
+    float x = 0.f;
+    if (k < p.K) x = p.transposed ? W[(size_t)n * p.ld + k] : W[(size_t)k * p.ld + n];
+    float hi, lo;
+    tc::split_tf32(x, hi, lo);
+    char* tile = reinterpret_cast<char*>(wpack + p.dst) + (size_t)kb * 2 * p.N * 128;
+    const uint32_t off = tc::sw128_offset((uint32_t)n, (uint32_t)kk);
+    *reinterpret_cast<float*>(tile + off) = hi;
+    *reinterpret_cast<float*>(tile + (size_t)p.N * 128 + off) = lo;
+  }
+}
+}  // namespace
+
 extern "C" int nmarl_pack_weights(const nmarl_model* m, const float* params, float* wt, float* wpack, void* stream) {
   NMARL_CHECK(m && params && wt && wpack, "pack_weights: missing buffers");
   cudaStream_t st = (cudaStream_t)stream;
-  const int SD = m->s_dim;
-  dim3 blk(32, 8);
-  for (int i = 0; i < m->n_agent; ++i) {
-    const nmarl_agent& ag = m->agent[i];
-    const int Kx = ag.x_nsrc * ag.x_w;
-    const int Km = (m->variant == NMARL_IC3) ? NH : ag.n_nbr * NH;
-    // transposed copies (also used by the FFMA backward)
-    tc_transpose_kernel<<<dim3(NG / 32, (SD + NH + 31) / 32), blk, 0, st>>>(params + ag.o_wxh, wt + ag.t_wxh, SD + NH, NG);
-    if (m->variant != NMARL_IA2C && Km > 0)
-      tc_transpose_kernel<<<dim3(2, (Km + 31) / 32), blk, 0, st>>>(params + ag.o_w_msg, wt + ag.t_w_msg, Km, NH);
-    if (m->variant == NMARL_DIAL) tc_transpose_kernel<<<dim3(2, 2), blk, 0, st>>>(params + ag.o_mfc_w, wt + ag.t_mfc, NH, NH);
-    // forward operands
-    if (nmarl_launch_pack_b(params + ag.o_w_ob, NH, Kx, 0, NH, wpack + ag.tp_x, st)) return 1;
-    if (m->variant == NMARL_NC && nmarl_launch_pack_b(params + ag.o_w_fp, NH, ag.n_nbr * m->n_a, 0, NH, wpack + ag.tp_p, st)) return 1;
-    if (m->variant != NMARL_IA2C && Km > 0 && nmarl_launch_pack_b(params + ag.o_w_msg, NH, Km, 0, NH, wpack + ag.tp_m, st)) return 1;
-    if (nmarl_launch_pack_b(params + ag.o_wxh, NG, SD + NH, 0, NG, wpack + ag.tp_g, st)) return 1;
-    if (m->variant == NMARL_DIAL && nmarl_launch_pack_b(params + ag.o_mfc_w, NH, NH, 0, NH, wpack + ag.tp_mfc, st)) return 1;
-    // backward operands (from the transposed copies)
-    if (nmarl_launch_pack_b(wt + ag.t_wxh, SD + NH, NG, 0, SD + NH, wpack + ag.tp_gT, st)) return 1;
-    if (m->variant != NMARL_IA2C && Km > 0 && nmarl_launch_pack_b(wt + ag.t_w_msg, Km, NH, 0, Km, wpack + ag.tp_mT, st)) return 1;
-    if (m->variant == NMARL_DIAL && nmarl_launch_pack_b(wt + ag.t_mfc, NH, NH, 0, NH, wpack + ag.tp_mfcT, st)) return 1;
+  pack_all_kernel<<<dim3(16, m->n_agent * PACK_JOBS), 256, 0, st>>>(*m, params, wpack);
+  NMARL_LAUNCH_CHECK();
+  if (m->variant == NMARL_DIAL) {          // DIAL's message-gradient kernel reads the plain transposed copies
+    dim3 blk(32, 8);
+    for (int i = 0; i < m->n_agent; ++i) {
+      const nmarl_agent& ag = m->agent[i];
+      const int Km = ag.n_nbr * NH;
+      if (Km > 0) tc_transpose_kernel<<<dim3(2, (Km + 31) / 32), blk, 0, st>>>(params + ag.o_w_msg, wt + ag.t_w_msg, Km, NH);
+      tc_transpose_kernel<<<dim3(2, 2), blk, 0, st>>>(params + ag.o_mfc_w, wt + ag.t_mfc, NH, NH);
+    }
+    NMARL_LAUNCH_CHECK();
   }
   return 0;
 }

@@ -169,20 +169,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     // round-to-nearest fp32 adds.
     const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;   // tcgen05.ld is warp-collective
     float* out = wsj + (size_t)ka * d.N;
+    // The previous partial sums are fetched BEFORE the wait for the segment's last MMAs (the loads do not depend on
+    // them) in two batches of four 8-column pieces, so that one L2 round trip, not eight, is exposed per drain.
     auto flush = [&](int seg) {
+      const bool mine = warp_active && (real || one);
+      const bool rmw = mine && seg > 0;
+      float4 p[8];
+      auto fetch = [&](int half) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int c0 = set * 8 + 8 * NSET * (4 * half + it);
+          if (rmw && c0 < d.N) {
+            p[2 * it] = *reinterpret_cast<const float4*>(out + c0);
+            p[2 * it + 1] = *reinterpret_cast<const float4*>(out + c0 + 4);
+          }
+        }
+      };
+      fetch(0);
       tc::mbar_wait(acc_full, seg & 1, k.err, 13);
       tc::fence_after_sync();
-      if (warp_active) {
-        for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) {
-          float v[8];
-          tc::tmem_ld8(tmem + c.lane_base + ACC_COL + c0, v);
-          tc::wait_ld();
-          if (real || one) {
-            if (seg > 0) {
-              const float4 p0 = *reinterpret_cast<const float4*>(out + c0), p1 = *reinterpret_cast<const float4*>(out + c0 + 4);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) fetch(1);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int c0 = set * 8 + 8 * NSET * (4 * half + it);
+          if (warp_active && c0 < d.N) {                       // warp-uniform: tcgen05.ld is warp-collective
+            float v[8];
+            tc::tmem_ld8(tmem + c.lane_base + ACC_COL + c0, v);
+            tc::wait_ld();
+            if (rmw) {
+              const float4 p0 = p[2 * it], p1 = p[2 * it + 1];
               v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
             }
-            store_vec<8>(out + c0, v);
+            if (mine) store_vec<8>(out + c0, v);
           }
         }
       }

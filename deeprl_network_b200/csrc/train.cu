@@ -596,8 +596,8 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
 
 // Heads + A2C loss terms + d(loss)/d(logits, v) from the saved h sequence (thread == env row); used when the
 // rollout already saved the cell activations.  Same arithmetic as the TRAIN epilogue of the forward kernels.
-struct HeadFwdK {                 // pointers are for step 0; blockIdx.z = t strides them
-  int B, N, loss_tiles, fm;
+struct HeadFwdK {                 // pointers are for step 0; t = t0 + blockIdx.z strides them
+  int B, N, loss_tiles, fm, t0;
   const float* params; const float* h1; const int32_t* act; const float* Rs; const float* Advs;
   float* sv_dlv; float* loss_part;
   float loss_scale, v_coef, e_coef;
@@ -605,7 +605,7 @@ struct HeadFwdK {                 // pointers are for step 0; blockIdx.z = t str
 
 __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant__ nmarl_model m, const __grid_constant__ HeadFwdK k) {
   __shared__ float red[3][4];
-  const int i = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x, B = k.B, t = blockIdx.z;
+  const int i = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x, B = k.B, t = k.t0 + blockIdx.z;
   const nmarl_agent& ag = m.agent[i];
   const int n_a = m.n_a;
   const float* __restrict__ P = k.params;
@@ -831,21 +831,25 @@ extern "C" int nmarl_a2c_train_forward(const nmarl_model* m, const nmarl_bwd_arg
   return 0;
 }
 
-extern "C" int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args* a, void* stream) {
-  if (check_bwd_args(m, a)) return 1;
-  cudaStream_t st = (cudaStream_t)stream;
+// heads + loss partials + d(loss)/d(logits, v) of time steps [t0, t0 + nt) from h_seq
+static int launch_train_heads(const nmarl_model* m, const nmarl_bwd_args* a, int t0, int nt, cudaStream_t st) {
+  if (nt <= 0) return 0;
   const int N = m->n_agent, B = a->B, T = a->T;
   const size_t nb = (size_t)N * B;
-  const int tiles = nmarl_fwd_tiles(B);
   HeadFwdK k{};
-  k.B = B; k.N = N; k.loss_tiles = tiles; k.params = a->params; k.fm = a->state_fm;
+  k.B = B; k.N = N; k.loss_tiles = nmarl_fwd_tiles(B); k.params = a->params; k.fm = a->state_fm; k.t0 = t0;
   k.h1 = a->h_seq + nb * NH;                                  // h after step t = h_seq[t + 1]
   k.act = a->act; k.Rs = a->Rs; k.Advs = a->Advs;
   k.sv_dlv = a->sv_dlv; k.loss_part = a->loss_part;
   k.loss_scale = 1.0f / ((float)T * (float)a->B_total); k.v_coef = a->v_coef; k.e_coef = a->e_coef;
-  train_heads_kernel<<<dim3((B + 127) / 128, N, T), 128, 0, st>>>(*m, k);
+  train_heads_kernel<<<dim3((B + 127) / 128, N, nt), 128, 0, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int nmarl_a2c_train_heads(const nmarl_model* m, const nmarl_bwd_args* a, void* stream) {
+  if (check_bwd_args(m, a)) return 1;
+  return launch_train_heads(m, a, 0, a->T, (cudaStream_t)stream);
 }
 
 extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, void* stream) {
@@ -855,7 +859,10 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   const size_t nb = (size_t)N * B;
   // 0. gradients of padding slots stay zero
   NMARL_CUDA(cudaMemsetAsync(a->grads, 0, (size_t)m->n_param * sizeof(float), st));
-  // 1. transposed weights
+  // 1. transposed weights for the FFMA backward kernels and DIAL's message-gradient kernel (the tensor-core cell
+  //    kernels read their own packed transposed operands, refreshed by nmarl_pack_weights)
+  const bool tc_path = (a->wpack != nullptr && B % 128 == 0 && m->kx_pad <= 32 && m->kp_pad <= 32);
+  if (!tc_path || m->variant == NMARL_DIAL)
   for (int i = 0; i < N; ++i) {
     const nmarl_agent& ag = m->agent[i];
     dim3 blk(32, 8);
@@ -878,8 +885,18 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
   NMARL_CHECK(a->ctx != nullptr, "a2c_bptt: nmarl_bwd_args.ctx is NULL (nmarl_create)");
   cudaStream_t side = a->ctx->side;
   cudaEvent_t ev_fork = a->ctx->fork, ev_join = a->ctx->join;
+  // fused_heads (saved-rollout path): the heads / loss kernel (nmarl_a2c_train_heads) is folded in.  Only the last
+  // HEAD_LEAD time steps are computed on the caller's stream before the reverse chain starts; the remaining steps run
+  // on the side stream beside the first reverse steps (the chain reaches step T-1-HEAD_LEAD long after they are done).
+  constexpr int HEAD_LEAD = 6;
+  const int lead = a->fused_heads ? (T < HEAD_LEAD ? T : HEAD_LEAD) : 0;
+  if (a->fused_heads && launch_train_heads(m, a, T - lead, lead, st)) return 1;
   NMARL_CUDA(cudaEventRecord(ev_fork, st));
   NMARL_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  if (a->fused_heads) {
+    if (launch_train_heads(m, a, 0, T - lead, side)) return 1;
+    NMARL_CUDA(cudaEventRecord(a->ctx->heads, side));
+  }
   {
     HeadK h{};
     h.N = N; h.B = B; h.T = T; h.splits = head_splits((long)B * T); h.n_a = m->n_a; h.fm = a->state_fm;
@@ -922,6 +939,7 @@ extern "C" int nmarl_a2c_bptt(const nmarl_model* m, const nmarl_bwd_args* a, voi
     k.ndp = nmarl_tc_ndp(m);
     k.dpT = (use_tc && a->sv_dpT) ? a->sv_dpT + (size_t)t * N * (B / 32) * (2 * k.ndp * 32) : nullptr;
     int rc = 0;
+    if (a->fused_heads && t == T - 1 - lead) NMARL_CUDA(cudaStreamWaitEvent(st, a->ctx->heads, 0));   // dlv of steps < T - lead
     if (a->ev_step) NMARL_CUDA(cudaEventRecord((cudaEvent_t)a->ev_step[2 * t], st));
     if (use_tc) rc = nmarl_tc_launch_bwd(m, k, st);
     else

@@ -226,6 +226,8 @@ typedef struct {
   void** ev_step;            /* optional timing hooks (bench.py): 2*T cudaEvent_t, recorded on `stream` before /
                                 after the cell kernel of reverse step t at [2t], [2t+1]; NULL = none               */
   void** ev_wgrad;           /* optional: 2 cudaEvent_t around the weight-gradient GEMM kernel; NULL = none         */
+  int32_t fused_heads;       /* nmarl_a2c_bptt also does the work of nmarl_a2c_train_heads (do not call it), most of it
+                                on the ctx's side stream beside the first reverse steps                              */
 } nmarl_bwd_args;
 
 int nmarl_loss_tiles(const nmarl_model* m, int B);       /* tiles per agent in loss_part      */
