@@ -398,8 +398,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
           double s = 0.0;
 #pragma unroll
           for (int cc = 0; cc < NMARL_MAX_NA; ++cc) { if (cc < n_a) s += (double)pi[cc]; cdf[cc] = s; }
+          if (a.sample_mode == NMARL_SAMPLE_UNIFORM) {
+            // host-supplied uniforms: np.random.choice's rule verbatim (cdf /= cdf[-1]; searchsorted(cdf, u, 'right'))
 #pragma unroll
-          for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += ((cdf[cc] / s) <= u) ? 1 : 0;
+            for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += ((cdf[cc] / s) <= u) ? 1 : 0;
+          } else {
+            // device Philox stream (no NumPy stream to reproduce): the same inverse-cdf draw without the four fp64
+            // divisions -- they are the longest dependent chain of the kernel's tail
+            const double us = u * s;
+#pragma unroll
+            for (int cc = 0; cc < NMARL_MAX_NA; ++cc) if (cc < n_a) act += (cdf[cc] <= us) ? 1 : 0;
+          }
           act = min(act, n_a - 1);
         }
         a.action[row] = act;

@@ -16,6 +16,10 @@ namespace {
 using namespace tcrow;
 
 enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_M0, J_ENC_M1, J_COUNT };
+// Row-thread roles: warp-sets 0,1 produce the A operand (16 of the 32 columns of a k-block each), warp-sets 2,3 derive
+// the `lo` half of the raw B tiles in shared memory; the two dependent chains (global load -> split -> tcgen05.st
+// and TMA wait -> lds/sts -> proxy fence) run side by side instead of back to back in every thread.
+constexpr int A_SETS = 2, A_THREADS = 128 * A_SETS, WA = 32 / A_SETS;
 constexpr int SEG_KB = 16;       // k-blocks (of 32 rows) accumulated in TMEM before the accumulator is drained (see flush)
 
 struct TcWgK {
@@ -87,12 +91,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
   if (tid == 0) {
     for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], ROW_THREADS); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], A_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::mbar_init(acc_free, ROW_THREADS);
     if constexpr (RAW)
-      for (int s = 0; s < S_STAGES; ++s) tc::mbar_init(&lo_full[s], ROW_THREADS);
+      for (int s = 0; s < S_STAGES; ++s) tc::mbar_init(&lo_full[s], ROW_THREADS - A_THREADS);
     tc::fence_barrier_init();
   }
   if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
@@ -133,33 +137,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     }
     // the A operand of k-block q: 8 consecutive envs of this thread's feature (global loads; issued one k-block AHEAD so
     // that their latency hides behind the lo pass / the barrier waits of the current k-block)
-    auto load_x = [&](int q, float (&x)[W]) {
+    auto load_x = [&](int q, float (&x)[WA]) {
       const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
       if (hs_agent >= 0) {
-        const float* src = k.h_seq + (((size_t)t * N_agents + hs_agent) * NH + hs_unit) * k.B + rb * 32 + set * W;
+        const float* src = k.h_seq + (((size_t)t * N_agents + hs_agent) * NH + hs_unit) * k.B + rb * 32 + set * WA;
 #pragma unroll
-        for (int p = 0; p < W / 4; ++p) {
+        for (int p = 0; p < WA / 4; ++p) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * p));
           x[4 * p] = v.x; x[4 * p + 1] = v.y; x[4 * p + 2] = v.z; x[4 * p + 3] = v.w;
         }
         if (hs_mask) {
-          const float* dn = k.done_pre + (size_t)t * k.B + rb * 32 + set * W;
+          const float* dn = k.done_pre + (size_t)t * k.B + rb * 32 + set * WA;
 #pragma unroll
-          for (int p = 0; p < W / 4; ++p) {
+          for (int p = 0; p < WA / 4; ++p) {
             const float4 v = __ldg(reinterpret_cast<const float4*>(dn + 4 * p));
             x[4 * p] *= 1.0f - v.x; x[4 * p + 1] *= 1.0f - v.y; x[4 * p + 2] *= 1.0f - v.z; x[4 * p + 3] *= 1.0f - v.w;
           }
         }
       } else if (real) {
-        const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * W;
+        const float* src = d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * WA;
 #pragma unroll
-        for (int p = 0; p < W / 4; ++p) {
+        for (int p = 0; p < WA / 4; ++p) {
           const float4 v = __ldcs(reinterpret_cast<const float4*>(src + 4 * p));
           x[4 * p] = v.x; x[4 * p + 1] = v.y; x[4 * p + 2] = v.z; x[4 * p + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < W; ++j) x[j] = one ? 1.0f : 0.0f;
+        for (int j = 0; j < WA; ++j) x[j] = one ? 1.0f : 0.0f;
       }
     };
     // Segmented accumulation.  The tensor core adds every MMA into the fp32 accumulator with round-toward-zero: a bias
@@ -209,30 +213,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       tc::fence_before_sync();
       tc::mbar_arrive(acc_free);
     };
-    float xn[W];
-    if (nkb > 0) load_x(0, xn);
-    for (int q = 0; q < nkb; ++q) {
-      float x[W];
+    if (set < A_SETS) {
+      // ---- A producers: columns [set * WA, set * WA + WA) of every k-block, loads issued one k-block ahead ------------
+      float xn[WA];
+      if (nkb > 0) load_x(0, xn);
+      for (int q = 0; q < nkb; ++q) {
+        float x[WA];
 #pragma unroll
-      for (int j = 0; j < W; ++j) x[j] = xn[j];
-      if (q + 1 < nkb) load_x(q + 1, xn);
-      produce_in(c, x);
-      if constexpr (RAW) {                                              // lo half of this k-block's B stage
-        const int st = q % S_STAGES;
-        tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 41);
-        const float4* raw = reinterpret_cast<const float4*>(bst + st * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(bst + st * STAGE_BYTES + tile_bytes);
-        for (uint32_t e = (uint32_t)tid; e < tile_bytes / 16; e += ROW_THREADS) {
-          const float4 v = raw[e];
-          float4 l;
-          l.x = tc::tf32_lo_of_raw(v.x); l.y = tc::tf32_lo_of_raw(v.y);
-          l.z = tc::tf32_lo_of_raw(v.z); l.w = tc::tf32_lo_of_raw(v.w);
-          lo[e] = l;
+        for (int j = 0; j < WA; ++j) x[j] = xn[j];
+        if (q + 1 < nkb) load_x(q + 1, xn);
+        produce_begin(c);
+#pragma unroll
+        for (int p = 0; p < WA / 8; ++p) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = x[8 * p + j];
+          produce_piece(c, set * WA + 8 * p, t8);
         }
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&lo_full[st]);
+        produce_end(c);
+        if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
       }
-      if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
+    } else {
+      // ---- lo derivation (RAW tiles): lo = rn_tf32(x - trunc_tf32(x)) of the k-block's B stage ---------------------------
+      const int lt = tid - A_THREADS;
+      for (int q = 0; q < nkb; ++q) {
+        if constexpr (RAW) {
+          const int st = q % S_STAGES;
+          tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 41);
+          const float4* raw = reinterpret_cast<const float4*>(bst + st * STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(bst + st * STAGE_BYTES + tile_bytes);
+          for (uint32_t e = (uint32_t)lt; e < tile_bytes / 16; e += ROW_THREADS - A_THREADS) {
+            const float4 v = raw[e];
+            float4 l;
+            l.x = tc::tf32_lo_of_raw(v.x); l.y = tc::tf32_lo_of_raw(v.y);
+            l.z = tc::tf32_lo_of_raw(v.z); l.w = tc::tf32_lo_of_raw(v.w);
+            lo[e] = l;
+          }
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&lo_full[st]);
+        }
+        if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
+      }
     }
     if (nkb == 0 && warp_active && (real || one)) {
       const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
