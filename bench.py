@@ -384,6 +384,7 @@ def dropin_b1(config, updates=3):
     cp = load_cfg(config, n_env=1)
     env = M.init_env(cp['ENV_CONFIG'])
     model = M.init_agent(env, cp['MODEL_CONFIG'], 10 ** 6, 12)
+    model.engine.world = 1                 # one process drives this API (rank 0 only): no gradient all-reduce
     tr = Trainer(env, model, Counter(10 ** 9, 10 ** 9, 10 ** 9), None)
     ob, done = env.reset(), True
     model.reset()

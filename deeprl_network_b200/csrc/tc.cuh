@@ -76,8 +76,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -86,7 +86,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return true;
-    if (clock64() - t0 > (1ll << 27)) break;
+    // The watchdog (clock + the grid-wide abort flag in global memory) is consulted only every 64th failed try_wait:
+    // a global load per poll keeps the thread away from the barrier for an L2 round trip (~700 cycles) and that
+    // latency was added to every wake-up of every fine-grained pipeline wait.
+    if ((spins & 63u) != 63u) continue;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > (1ll << 27)) break;
     if (err != nullptr && *reinterpret_cast<volatile int*>(err) != 0) return false;
   }
   if (err != nullptr) atomicCAS(err, 0, code);

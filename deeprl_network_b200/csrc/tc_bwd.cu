@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
     int n = 0;
-    for (int kb = 0; kb < 8; ++kb) sched[n++] = make_kb(ag.tp_gT, SD + NH, NG, kb, 0, kb == 0, 0, kb == 7);
+    // dgrad k-blocks in the order the row threads produce dz: gate o first (its inputs are already in registers from
+    // the dc computation), then i and u (which share their two loads), then f
+    const int korder[8] = {4, 5, 0, 1, 6, 7, 2, 3};
+    for (int q = 0; q < 8; ++q) sched[n++] = make_kb(ag.tp_gT, SD + NH, NG, korder[q], 0, q == 0, 0, q == 7);
     if (VAR != NMARL_IA2C && Km > 0)
       for (int kb = 0; kb < 2; ++kb) sched[n++] = make_kb(ag.tp_mT, Km, NH, kb, 0, kb == 0, 0, kb == 1);
     *n_kb_s = n;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
     const float* enc_fm = k.sv_enc ? k.sv_enc + (size_t)i * 128 * B : nullptr;
 
     // ---- total dh and dc for the thread's units --------------------------------------------------------------
-    float dh[EW], dct[EW];
+    float dh[EW], dct[EW], dzo[EW];
     {
       const float4 d0 = *reinterpret_cast<const float4*>(k.sv_dlv + row * 8);
       const float4 d1 = *reinterpret_cast<const float4*>(k.sv_dlv + row * 8 + 4);
@@ -110,39 +113,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       for (int j = 0; j < EW; ++j) {
         const float tcv = ftanh(ccv[j]);
         dct[j] += dh[j] * gov[j] * (1.0f - tcv * tcv);
+        dzo[j] = dh[j] * tcv * gov[j] * (1.0f - gov[j]);          // dz of gate o, produced first below
       }
     }
-    // ---- gate derivatives, gate by gate = k-block pair by k-block pair of the dgrad A operand -----------------
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float dz[EW];
-      if (g == 0 || g == 3) {
-        float gi[EW], gu[EW];
-        ld_fm<EW>(gates_fm, 0 * NH + e0, B, b, gi);
-        ld_fm<EW>(gates_fm, 3 * NH + e0, B, b, gu);
-#pragma unroll
-        for (int j = 0; j < EW; ++j)
-          dz[j] = (g == 0) ? dct[j] * gu[j] * gi[j] * (1.0f - gi[j]) : dct[j] * gi[j] * (1.0f - gu[j] * gu[j]);
-      } else if (g == 1) {
-        float gf[EW], cpv[EW], dcp[EW];
-        ld_fm<EW>(gates_fm, 1 * NH + e0, B, b, gf);
-        ld_state<FM, EW>(k.c_prev, (size_t)i, b, e0, B, cpv);
-#pragma unroll
-        for (int j = 0; j < EW; ++j) {
-          dz[j] = dct[j] * (cpv[j] * nd) * gf[j] * (1.0f - gf[j]);
-          dcp[j] = dct[j] * gf[j] * nd;
-        }
-        st_state<FM, EW>(k.dc_out, (size_t)i, b, e0, B, dcp);
-      } else {
-        float go[EW], ccv[EW];
-        ld_fm<EW>(gates_fm, 2 * NH + e0, B, b, go);
-        ld_state<FM, EW>(k.c_cur, (size_t)i, b, e0, B, ccv);
-#pragma unroll
-        for (int j = 0; j < EW; ++j) {
-          const float tcv = ftanh(ccv[j]);
-          dz[j] = dh[j] * tcv * go[j] * (1.0f - go[j]);
-        }
-      }
+    // ---- gate derivatives: per gate the bias partial sums, the dz^T operand tile for the weight-gradient GEMM and the
+    // two dgrad A k-blocks.  Order o, i, u, f (see the k-block schedule above): every saved gate is loaded once.
+    auto emit = [&](const int g, const float (&dz)[EW]) {
       {   // gate-bias gradient = column sums of dz: sum over this warp's 32 rows by recursive halving (16 shuffles per
           // gate instead of a feature-major copy of dz in HBM + a separate column-sum kernel)
         float a[EW];
@@ -177,7 +153,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
           }
         }
       }
-      produce_act(c, dz);                      // k-blocks 2g, 2g+1 of the 256-deep contraction
+      produce_act(c, dz);                      // the gate's two k-blocks of the 256-deep dgrad contraction
+    };
+    emit(2, dzo);
+    {
+      float gi[EW], gu[EW], dz[EW];
+      ld_fm<EW>(gates_fm, 0 * NH + e0, B, b, gi);
+      ld_fm<EW>(gates_fm, 3 * NH + e0, B, b, gu);
+#pragma unroll
+      for (int j = 0; j < EW; ++j) dz[j] = dct[j] * gu[j] * gi[j] * (1.0f - gi[j]);
+      emit(0, dz);
+#pragma unroll
+      for (int j = 0; j < EW; ++j) dz[j] = dct[j] * gi[j] * (1.0f - gu[j] * gu[j]);
+      emit(3, dz);
+    }
+    {
+      float gf[EW], cpv[EW], dcp[EW], dz[EW];
+      ld_fm<EW>(gates_fm, 1 * NH + e0, B, b, gf);
+      ld_state<FM, EW>(k.c_prev, (size_t)i, b, e0, B, cpv);
+#pragma unroll
+      for (int j = 0; j < EW; ++j) {
+        dz[j] = dct[j] * (cpv[j] * nd) * gf[j] * (1.0f - gf[j]);
+        dcp[j] = dct[j] * gf[j] * nd;
+      }
+      st_state<FM, EW>(k.dc_out, (size_t)i, b, e0, B, dcp);
+      emit(1, dz);
     }
 
     // per-tile gate-bias partial sums (fixed order over the four row quarters), reduced over (t, tile) afterwards
