@@ -20,6 +20,12 @@ enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_M0, J_ENC_M1, J_COUNT };
 // the `lo` half of the raw B tiles in shared memory; the two dependent chains (global load -> split -> tcgen05.st
 // and TMA wait -> lds/sts -> proxy fence) run side by side instead of back to back in every thread.
 constexpr int A_SETS = 2, A_THREADS = 128 * A_SETS, WA = 32 / A_SETS;
+// Shared-memory rings.  RAW tiles: WG_RAW_STAGES single 32 KB raw tiles (bulk-copied, deep enough to cover the DRAM
+// latency of a 32 KB copy at one k-block per ~0.8 us) + WG_LO_BUFS derived `lo` tiles; [hi | lo] pairs: S_STAGES x 64 KB.
+constexpr int WG_RAW_STAGES = 5, WG_LO_BUFS = 2;
+constexpr uint32_t WG_RAW_BYTES = 256 * 128;
+constexpr size_t WG_SMEM_RAW = (size_t)(WG_RAW_STAGES + WG_LO_BUFS) * WG_RAW_BYTES + 1024 + 32 * 8 + 64;
+static_assert(WG_SMEM_RAW <= 232448, "wgrad RAW ring exceeds the 227 KB of dynamic shared memory");
 constexpr int SEG_KB = 16;       // k-blocks (of 32 rows) accumulated in TMEM before the accumulator is drained (see flush)
 
 struct TcWgK {
@@ -70,12 +76,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bst = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_STAGES * STAGE_BYTES);
-  uint64_t* b_full = bars, *b_empty = bars + S_STAGES, *a_full = bars + 2 * S_STAGES, *a_empty = a_full + A_SLOTS;
+  constexpr int NST = RAW ? WG_RAW_STAGES : S_STAGES;                  // B stages
+  constexpr uint32_t STB = RAW ? WG_RAW_BYTES : STAGE_BYTES;           // bytes per B stage
+  uint8_t* lobuf = smem + (size_t)NST * STB;                           // RAW only: WG_LO_BUFS derived lo tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * STB + (RAW ? WG_LO_BUFS * WG_RAW_BYTES : 0));
+  uint64_t* b_full = bars, *b_empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + A_SLOTS;
   uint64_t* enc_full = a_empty + A_SLOTS, *acc_full = enc_full + 1;
-  uint64_t* lo_full = acc_full + 1;                                    // RAW only: S_STAGES barriers
-  uint64_t* acc_free = acc_full + 1 + S_STAGES;                        // accumulator drained by the row threads (segment flush)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+  uint64_t* acc_free = acc_full + 1;                                   // accumulator drained by the row threads (segment flush)
+  uint64_t* lo_full = acc_free + 1, *lo_empty = lo_full + WG_LO_BUFS;  // RAW only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + WG_LO_BUFS);
 
   const int sp = blockIdx.x, jslot = blockIdx.y, i = blockIdx.z;
   const int kind = k.jobs[jslot];
@@ -90,13 +99,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   float* wsj = k.ws + k.ws_off[jslot] + ((size_t)sp * N_agents + i) * 128 * d.N;
 
   if (tid == 0) {
-    for (int s = 0; s < S_STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < A_SLOTS; ++s) { tc::mbar_init(&a_full[s], A_THREADS); tc::mbar_init(&a_empty[s], 1); }
     tc::mbar_init(enc_full, 1);
     tc::mbar_init(acc_full, 1);
     tc::mbar_init(acc_free, ROW_THREADS);
     if constexpr (RAW)
-      for (int s = 0; s < S_STAGES; ++s) tc::mbar_init(&lo_full[s], ROW_THREADS - A_THREADS);
+      for (int s = 0; s < WG_LO_BUFS; ++s) { tc::mbar_init(&lo_full[s], ROW_THREADS - A_THREADS); tc::mbar_init(&lo_empty[s], 1); }
     tc::fence_barrier_init();
   }
   if (warp == ROW_THREADS / 32 + 1) tc::tmem_alloc(tmem_slot, 512);
@@ -238,10 +247,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       const int lt = tid - A_THREADS;
       for (int q = 0; q < nkb; ++q) {
         if constexpr (RAW) {
-          const int st = q % S_STAGES;
-          tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 41);
-          const float4* raw = reinterpret_cast<const float4*>(bst + st * STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(bst + st * STAGE_BYTES + tile_bytes);
+          const int st = q % NST, lb = q % WG_LO_BUFS;
+          tc::mbar_wait(&lo_empty[lb], ((q / WG_LO_BUFS) & 1) ^ 1, k.err, 42);      // the MMAs that read this lo buffer are done
+          tc::mbar_wait(&b_full[st], (q / NST) & 1, k.err, 41);
+          const float4* raw = reinterpret_cast<const float4*>(bst + (size_t)st * STB);
+          float4* lo = reinterpret_cast<float4*>(lobuf + (size_t)lb * WG_RAW_BYTES);
           for (uint32_t e = (uint32_t)lt; e < tile_bytes / 16; e += ROW_THREADS - A_THREADS) {
             const float4 v = raw[e];
             float4 l;
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
             lo[e] = l;
           }
           tc::fence_proxy_async();
-          tc::mbar_arrive(&lo_full[st]);
+          tc::mbar_arrive(&lo_full[lb]);
         }
         if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
       }
@@ -262,17 +272,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   } else if (warp == ROW_THREADS / 32) {
     if (tc::elect_one()) {
       for (int q = 0; q < nkb; ++q) {
-        const int kb = kb0 + q, st = q % S_STAGES;
+        const int kb = kb0 + q, st = q % NST;
         const int t = kb / bpt, rb = kb - t * bpt;
-        tc::mbar_wait(&b_empty[st], ((q / S_STAGES) & 1) ^ 1, k.err, 21);
+        tc::mbar_wait(&b_empty[st], ((q / NST) & 1) ^ 1, k.err, 21);
         const uint8_t* tile = bt_tile(t, rb);
         if constexpr (RAW) {
           tc::mbar_arrive_expect_tx(&b_full[st], tile_bytes);
-          tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
+          tc::bulk_g2s(bst + (size_t)st * STB, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
         } else {
           tc::mbar_arrive_expect_tx(&b_full[st], 2 * tile_bytes);
-          tc::bulk_g2s(bst + st * STAGE_BYTES, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
-          tc::bulk_g2s(bst + st * STAGE_BYTES + tile_bytes, tile + (size_t)(d.tile_rows + d.n_row0) * 128, tile_bytes, &b_full[st]);
+          tc::bulk_g2s(bst + (size_t)st * STB, tile + (size_t)d.n_row0 * 128, tile_bytes, &b_full[st]);
+          tc::bulk_g2s(bst + (size_t)st * STB + tile_bytes, tile + (size_t)(d.tile_rows + d.n_row0) * 128, tile_bytes, &b_full[st]);
         }
       }
     }
@@ -280,14 +290,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)d.N);
       for (int q = 0; q < nkb; ++q) {
-        const int st = q % S_STAGES, slot = q & (A_SLOTS - 1);
+        const int st = q % NST, slot = q & (A_SLOTS - 1), lb = q % WG_LO_BUFS;
         const int seg = q / SEG_KB;
         const bool seg_first = (q % SEG_KB) == 0;
         if (seg_first && seg > 0) tc::mbar_wait(acc_free, (seg - 1) & 1, k.err, 34);   // previous segment drained
-        tc::mbar_wait(&b_full[st], (q / S_STAGES) & 1, k.err, 31);
+        tc::mbar_wait(&b_full[st], (q / NST) & 1, k.err, 31);
         tc::mbar_wait(&a_full[slot], (q / A_SLOTS) & 1, k.err, 32);
         tc::fence_after_sync();
-        const uint64_t d_hi = tc::smem_desc_sw128(bst + st * STAGE_BYTES), d_lo = tc::smem_desc_sw128(bst + st * STAGE_BYTES + tile_bytes);
+        const uint64_t d_hi = tc::smem_desc_sw128(bst + (size_t)st * STB);
+        const uint64_t d_lo = tc::smem_desc_sw128(RAW ? lobuf + (size_t)lb * WG_RAW_BYTES : bst + (size_t)st * STB + tile_bytes);
         if constexpr (RAW) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {                              // passes that need only the raw tile
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
             tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_hi + 2 * ks, idesc, (seg_first && ks == 0) ? 0u : 1u);
             tc::mma_tf32_ts(tmem + ACC_COL, a_lo, d_hi + 2 * ks, idesc, 1u);
           }
-          tc::mbar_wait(&lo_full[st], (q / S_STAGES) & 1, k.err, 33);
+          tc::mbar_wait(&lo_full[lb], (q / WG_LO_BUFS) & 1, k.err, 33);
           tc::fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
@@ -311,6 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         }
         tc::mma_commit(&a_empty[slot]);
         tc::mma_commit(&b_empty[st]);
+        if constexpr (RAW) tc::mma_commit(&lo_empty[lb]);
         if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) tc::mma_commit(acc_full);
       }
     }
@@ -412,13 +424,13 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
   static bool configured = false;
   if (!configured) {
     NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    NMARL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_RAW));
     configured = true;
   }
   gate_bias_reduce_kernel<<<dim3(NG / 32, m->n_agent), 256, 0, st_bias>>>(*m, sv_dz, B / 128, T, grads);   // independent of the GEMM jobs
   NMARL_LAUNCH_CHECK();
   if (ev_wgrad) NMARL_CUDA(cudaEventRecord((cudaEvent_t)ev_wgrad[0], st));
-  if (raw_tiles) tc_wgrad_kernel<true><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
+  if (raw_tiles) tc_wgrad_kernel<true><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, WG_SMEM_RAW, st>>>(*m, k);
   else tc_wgrad_kernel<false><<<dim3(k.splits, k.n_jobs, m->n_agent), TC_THREADS, TC_SMEM, st>>>(*m, k);
   NMARL_LAUNCH_CHECK();
   if (ev_wgrad) NMARL_CUDA(cudaEventRecord((cudaEvent_t)ev_wgrad[1], st));
