@@ -12,6 +12,8 @@
 #include "bwd_common.cuh"
 #include "tc_row.cuh"
 
+extern long long* g_nmarl_prof;          // api.cu: debug hook (nmarl_debug_set_prof)
+
 namespace {
 using namespace tcrow;
 
@@ -36,6 +38,7 @@ struct TcWgK {
   long long ws_off[J_COUNT];     // float offset of each job's partial block [splits][N_agents][128][N_job]
   int jobs[J_COUNT]; int n_jobs; // job kinds present
   int* err;
+  long long* prof;               // debug: clock64 stamps of CTA (split 1, job 0, agent 1) or NULL (tools/wg_prof.py)
 };
 
 struct JobDesc {
@@ -181,56 +184,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     // (192 MMAs) and the segment sums are added up in registers / the CTA's own workspace slot with ordinary
     // round-to-nearest fp32 adds.
     const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;   // tcgen05.ld is warp-collective
-    float* out = wsj + (size_t)ka * d.N;
+    float* out = wsj + ka;                                      // element (ka, n) of the partial block at out[n * 128]
     // The previous partial sums are fetched BEFORE the wait for the segment's last MMAs (the loads do not depend on
     // them) in two batches of four 8-column pieces, so that one L2 round trip, not eight, is exposed per drain.
+    long long* prof = (k.prof != nullptr && sp == 1 && jslot == 0 && i == 1 && (tid == 0 || tid == A_THREADS)) ? k.prof + (tid ? 128 : 192) : nullptr;
     auto flush = [&](int seg) {
+      if (prof && seg < 5) prof[3 * seg] = clock64();
       const bool mine = warp_active && (real || one);
       const bool rmw = mine && seg > 0;
-      float4 p[8];
-      auto fetch = [&](int half) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int c0 = set * 8 + 8 * NSET * (4 * half + it);
-          if (rmw && c0 < d.N) {
-            p[2 * it] = *reinterpret_cast<const float4*>(out + c0);
-            p[2 * it + 1] = *reinterpret_cast<const float4*>(out + c0 + 4);
-          }
-        }
-      };
-      fetch(0);
       tc::mbar_wait(acc_full, seg & 1, k.err, 13);
       tc::fence_after_sync();
+      if (prof && seg < 5) prof[3 * seg + 1] = clock64();
+      // workspace block layout [column n][lane ka]: for a fixed column the 32 lanes of a warp are 128 contiguous bytes
+#pragma unroll 2
+      for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) {
+        if (warp_active) {                                         // warp-uniform: tcgen05.ld is warp-collective
+          float pv[8];
+          if (rmw) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1) fetch(1);
+            for (int j = 0; j < 8; ++j) pv[j] = out[(size_t)(c0 + j) * 128];
+          }
+          float v[8];
+          tc::tmem_ld8(tmem + c.lane_base + ACC_COL + c0, v);
+          tc::wait_ld();
+          if (mine) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int c0 = set * 8 + 8 * NSET * (4 * half + it);
-          if (warp_active && c0 < d.N) {                       // warp-uniform: tcgen05.ld is warp-collective
-            float v[8];
-            tc::tmem_ld8(tmem + c.lane_base + ACC_COL + c0, v);
-            tc::wait_ld();
-            if (rmw) {
-              const float4 p0 = p[2 * it], p1 = p[2 * it + 1];
-              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-            }
-            if (mine) store_vec<8>(out + c0, v);
+            for (int j = 0; j < 8; ++j) out[(size_t)(c0 + j) * 128] = rmw ? v[j] + pv[j] : v[j];
           }
         }
       }
       tc::fence_before_sync();
+      if (prof && seg < 5) prof[3 * seg + 2] = clock64();
       tc::mbar_arrive(acc_free);
     };
     if (set < A_SETS) {
       // ---- A producers: columns [set * WA, set * WA + WA) of every k-block, loads issued one k-block ahead ------------
-      float xn[WA];
-      if (nkb > 0) load_x(0, xn);
-      for (int q = 0; q < nkb; ++q) {
-        float x[WA];
-#pragma unroll
-        for (int j = 0; j < WA; ++j) x[j] = xn[j];
-        if (q + 1 < nkb) load_x(q + 1, xn);
+      float xa[WA], xb[WA];                     // the operands of the next two k-blocks (two loads in flight per thread)
+      auto emit_a = [&](int q, float (&x)[WA]) {
         produce_begin(c);
 #pragma unroll
         for (int p = 0; p < WA / 8; ++p) {
@@ -240,7 +230,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
           produce_piece(c, set * WA + 8 * p, t8);
         }
         produce_end(c);
+        if (q + 2 < nkb) load_x(q + 2, x);        // refill this buffer; it is consumed two k-blocks from now
         if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
+      };
+      if (nkb > 0) load_x(0, xa);
+      if (nkb > 1) load_x(1, xb);
+      for (int q = 0; q < nkb; q += 2) {
+        emit_a(q, xa);
+        if (q + 1 < nkb) emit_a(q + 1, xb);
       }
     } else {
       // ---- lo derivation (RAW tiles): lo = rn_tf32(x - trunc_tf32(x)) of the k-block's B stage ---------------------------
@@ -266,8 +263,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       }
     }
     if (nkb == 0 && warp_active && (real || one)) {
-      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) store_vec<8>(out + c0, z);
+      for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET)
+        for (int j = 0; j < 8; ++j) out[(size_t)(c0 + j) * 128] = 0.f;
     }
   } else if (warp == ROW_THREADS / 32) {
     if (tc::elect_one()) {
@@ -289,8 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   } else {
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_tf32(128, (uint32_t)d.N);
+      long long* iprof = (k.prof != nullptr && sp == 1 && jslot == 0 && i == 1) ? k.prof : nullptr;
       for (int q = 0; q < nkb; ++q) {
         const int st = q % NST, slot = q & (A_SLOTS - 1), lb = q % WG_LO_BUFS;
+        if (iprof && q < 40) iprof[3 * q] = clock64();
         const int seg = q / SEG_KB;
         const bool seg_first = (q % SEG_KB) == 0;
         if (seg_first && seg > 0) tc::mbar_wait(acc_free, (seg - 1) & 1, k.err, 34);   // previous segment drained
@@ -306,8 +305,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
             tc::mma_tf32_ts(tmem + ACC_COL, a_hi, d_hi + 2 * ks, idesc, (seg_first && ks == 0) ? 0u : 1u);
             tc::mma_tf32_ts(tmem + ACC_COL, a_lo, d_hi + 2 * ks, idesc, 1u);
           }
+          if (iprof && q < 40) iprof[3 * q + 1] = clock64();
           tc::mbar_wait(&lo_full[lb], (q / WG_LO_BUFS) & 1, k.err, 33);
           tc::fence_after_sync();
+          if (iprof && q < 40) iprof[3 * q + 2] = clock64();
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             tc::mma_tf32_ts(tmem + ACC_COL, tmem + A_COL + slot * 64 + ks * 8, d_lo + 2 * ks, idesc, 1u);
@@ -338,11 +339,12 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const __grid_const
   const JobDesc d = job_desc(m, k, kind, i);
   const nmarl_agent& ag = m.agent[i];
   const int lanes = d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;
-  const int total = lanes * d.N;
+  const int total = 128 * d.N;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int ln = e / d.N, n = e - ln * d.N;
+    const int ln = e & 127, n = e >> 7;                      // partial blocks are [column n][lane]: coalesced over lanes
+    if (ln >= lanes) continue;
     float s = 0.f;
-    for (int sp = 0; sp < k.splits; ++sp) s += k.ws[k.ws_off[jslot] + (((size_t)sp * m.n_agent + i) * 128 + ln) * d.N + n];
+    for (int sp = 0; sp < k.splits; ++sp) s += k.ws[k.ws_off[jslot] + (((size_t)sp * m.n_agent + i) * d.N + n) * 128 + ln];
     if (kind == J_GATE0 || kind == J_GATE1) grads[ag.o_wxh + (size_t)(128 * (kind - J_GATE0) + ln) * NG + n] = s;
     else if (kind == J_ENC_X) {
       if (ln < d.ka_cnt) { if (n < NH) grads[ag.o_w_ob + ln * NH + n] = s; }
@@ -418,6 +420,7 @@ int nmarl_tc_launch_wgrads(const nmarl_model* m, int B, int T, const float* sv_s
   k.B = B; k.T = T; k.splits = nmarl_tc_wgrad_splits(m->n_agent); k.ndp = nmarl_tc_ndp(m);
   k.sv_sh = sv_sh; k.sv_xin = sv_xin; k.dzT = dzT; k.dpT = dpT; k.ws = ws; k.err = err;
   k.h_seq = h_seq; k.done_pre = done_pre;
+  k.prof = g_nmarl_prof;
   k.n_jobs = job_list(m, k.jobs);
   long long off = 0;
   for (int j = 0; j < k.n_jobs; ++j) { k.ws_off[j] = off; off += (long long)k.splits * m->n_agent * 128 * job_N(m, k.jobs[j]); }
