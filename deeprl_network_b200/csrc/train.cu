@@ -464,15 +464,52 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __grid_constant__
   const nmarl_agent& ag = m.agent[i];
   const int tid = threadIdx.x, u = tid & 63, part = tid >> 6;
   const long R = (long)k.T * k.B;
+  long r_begin, r_end;
+  if (k.fm) {
+    // feature-major h ([t][agent][unit][env]): the coalesced direction is env, so a warp covers 32 consecutive envs and
+    // 8 of the 64 units; 8 x 8 accumulators per thread, one shuffle tree over the envs at the end.  (Reading it with
+    // lanes = units touched 32 different 128-byte lines per load: 0.94 ms for 0.5 GB.)
+    const long nb32 = R / 32, per32 = (nb32 + k.splits - 1) / k.splits;
+    const long blk_begin = (long)sp * per32, blk_end = min(nb32, blk_begin + per32);
+    r_begin = blk_begin * 32; r_end = blk_end * 32;
+    const int lane = tid & 31, w = tid >> 5;
+    float a[8][8];
+#pragma unroll
+    for (int uu = 0; uu < 8; ++uu)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[uu][c] = 0.f;
+    for (long blk = blk_begin; blk < blk_end; ++blk) {
+      const long r = blk * 32 + lane, t = r / k.B, b = r - t * k.B;
+      const size_t row = ((size_t)t * k.N + i) * k.B + b;
+      const float4 d0 = *reinterpret_cast<const float4*>(k.dlv + row * 8);
+      const float4 d1 = *reinterpret_cast<const float4*>(k.dlv + row * 8 + 4);
+      const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      const float* hp = k.h1 + (((size_t)t * k.N + i) * NH + 8 * w) * k.B + b;
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        const float hv = hp[(size_t)uu * k.B];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[uu][c] = fmaf(hv, dl[c], a[uu][c]);
+      }
+    }
+#pragma unroll
+    for (int uu = 0; uu < 8; ++uu)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float x = a[uu][c];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) { red[0][8 * w + uu][c] = x; red[1][8 * w + uu][c] = 0.f; red[2][8 * w + uu][c] = 0.f; red[3][8 * w + uu][c] = 0.f; }
+      }
+  } else {
   const long per = (R + k.splits - 1) / k.splits;
-  const long r_begin = (long)sp * per, r_end = min(R, r_begin + per);
+  r_begin = (long)sp * per; r_end = min(R, r_begin + per);
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
   for (long r = r_begin + part; r < r_end; r += 4) {
     const long t = r / k.B, b = r - t * k.B;
     const size_t row = ((size_t)t * k.N + i) * k.B + b;
-    const float hv = k.fm ? k.h1[(((size_t)t * k.N + i) * NH + u) * k.B + b] : k.h1[row * NH + u];
+    const float hv = k.h1[row * NH + u];
     const float4 d0 = *reinterpret_cast<const float4*>(k.dlv + row * 8);
     const float4 d1 = *reinterpret_cast<const float4*>(k.dlv + row * 8 + 4);
     acc[0] = fmaf(hv, d0.x, acc[0]); acc[1] = fmaf(hv, d0.y, acc[1]); acc[2] = fmaf(hv, d0.z, acc[2]); acc[3] = fmaf(hv, d0.w, acc[3]);
@@ -480,6 +517,7 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __grid_constant__
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) red[part][u][c] = acc[c];
+  }
   // bias sums (8) and one-hot sums (n_nbr x n_a): every thread strides over the rows, then a fixed-order
   // block reduction (warp shuffle tree + per-warp partials summed in warp order)
   constexpr int NX = 8 + NMARL_MAX_NBR * NMARL_MAX_NA;
@@ -626,14 +664,21 @@ __global__ void __launch_bounds__(128) train_heads_kernel(const __grid_constant_
       } else {
         h4 = *reinterpret_cast<const float4*>(k.h1 + row * NH + 4 * q);
       }
+      const float4 vw = __ldg(reinterpret_cast<const float4*>(P + ag.o_v_w) + q);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float hv = f4get(h4, j);
         const int u = 4 * q + j;
+        if (n_a == 4) {                                   // one 16-byte load per unit instead of four scalar ones
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(P + ag.o_pi_w) + u);
+          logit[0] = fmaf(hv, w4.x, logit[0]); logit[1] = fmaf(hv, w4.y, logit[1]);
+          logit[2] = fmaf(hv, w4.z, logit[2]); logit[3] = fmaf(hv, w4.w, logit[3]);
+        } else {
 #pragma unroll
-        for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
-          if (cc < n_a) logit[cc] = fmaf(hv, __ldg(P + ag.o_pi_w + u * n_a + cc), logit[cc]);
-        v = fmaf(hv, __ldg(P + ag.o_v_w + u), v);
+          for (int cc = 0; cc < NMARL_MAX_NA; ++cc)
+            if (cc < n_a) logit[cc] = fmaf(hv, __ldg(P + ag.o_pi_w + u * n_a + cc), logit[cc]);
+        }
+        v = fmaf(hv, f4get(vw, j), v);
       }
     }
     float pi[NMARL_MAX_NA];
