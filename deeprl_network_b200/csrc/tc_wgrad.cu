@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       tc::fence_after_sync();
       if (prof && seg < 5) prof[3 * seg + 1] = clock64();
       // workspace block layout [column n][lane ka]: for a fixed column the 32 lanes of a warp are 128 contiguous bytes
-#pragma unroll 4
+#pragma unroll 2
       for (int c0 = set * 8; c0 < d.N; c0 += 8 * NSET) {
         if (warp_active) {                                         // warp-uniform: tcgen05.ld is warp-collective
           float pv[8];
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     };
     if (set < A_SETS) {
       // ---- A producers: columns [set * WA, set * WA + WA) of every k-block, loads issued one k-block ahead ------------
-      float xa[WA], xb[WA], xc[WA];            // the operands of the next three k-blocks: three loads in flight per thread
-      auto emit_a = [&](int q, float (&x)[WA]) {   // (the A stream is latency-bound: bytes in flight, not bandwidth)
+      float xa[WA], xb[WA];                     // the operands of the next two k-blocks (two loads in flight per thread)
+      auto emit_a = [&](int q, float (&x)[WA]) {
         produce_begin(c);
 #pragma unroll
         for (int p = 0; p < WA / 8; ++p) {
@@ -230,16 +230,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
           produce_piece(c, set * WA + 8 * p, t8);
         }
         produce_end(c);
-        if (q + 3 < nkb) load_x(q + 3, x);        // refill this buffer; it is consumed three k-blocks from now
+        if (q + 2 < nkb) load_x(q + 2, x);        // refill this buffer; it is consumed two k-blocks from now
         if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
       };
       if (nkb > 0) load_x(0, xa);
       if (nkb > 1) load_x(1, xb);
-      if (nkb > 2) load_x(2, xc);
-      for (int q = 0; q < nkb; q += 3) {
+      for (int q = 0; q < nkb; q += 2) {
         emit_a(q, xa);
         if (q + 1 < nkb) emit_a(q + 1, xb);
-        if (q + 2 < nkb) emit_a(q + 2, xc);
       }
     } else {
       // ---- lo derivation (RAW tiles): lo = rn_tf32(x - trunc_tf32(x)) of the k-block's B stage ---------------------------
