@@ -12,9 +12,10 @@ import sys
 tag = sys.argv[1]
 os.makedirs('profiles', exist_ok=True)
 
-# ---- launch list -------------------------------------------------------------------------------
-path = 'gpurun_out/launches_%s.csv' % tag
-if os.path.exists(path):
+# ---- launch lists (headline + one per BASELINE configuration: launches_<tag>_<cfg>.csv) --------------------
+import glob
+for path in sorted(glob.glob('gpurun_out/launches_%s*.csv' % tag)):
+    suffix = os.path.basename(path)[len('launches_%s' % tag):-4]          # '' or '_cfg3' ...
     lines = [l for l in open(path) if not l.startswith('==')]
     agg = collections.OrderedDict()
     n = 0
@@ -25,13 +26,17 @@ if os.path.exists(path):
         v = {'ns': v / 1e3, 'us': v, 'ms': v * 1e3}[r['Metric Unit']]
         name = re.sub(r'\(.*', '', r['Kernel Name']).replace('void ', '').replace('<unnamed>::', '')
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; n += 1
+    if not n:
+        continue
     tot = sum(a[1] for a in agg.values())
-    with open('profiles/%s_launches.txt' % tag, 'w') as f:
+    out = 'profiles/%s%s_launches.txt' % (tag, suffix)
+    with open(out, 'w') as f:
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n')
-        f.write('# command: python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e ; %d launches, %.0f us total\n' % (n, tot))
+        f.write('# command: python bench.py [--config ... --n-env ...] --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra ; %d launches, %.0f us total\n' % (n, tot))
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('%-75s n=%5d total=%10.0f us avg=%9.1f us share=%5.1f%%\n' % (k[:75], c, t, t / c, 100 * t / tot))
-    print(open('profiles/%s_launches.txt' % tag).read())
+    if not suffix:
+        print(open(out).read())
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
