@@ -24,12 +24,9 @@ enum { J_GATE0 = 0, J_GATE1, J_ENC_X, J_ENC_M0, J_ENC_M1, J_COUNT };
 constexpr int A_SETS = 2, A_THREADS = 128 * A_SETS, WA = 32 / A_SETS;
 // Shared-memory rings.  RAW tiles: WG_RAW_STAGES single 32 KB raw tiles (bulk-copied, deep enough to cover the DRAM
 // latency of a 32 KB copy at one k-block per ~0.8 us) + WG_LO_BUFS derived `lo` tiles; [hi | lo] pairs: S_STAGES x 64 KB.
-// The A operand (feature-major activations, 64 bytes per thread and k-block) is prefetched WG_A_DEPTH k-blocks ahead with
-// cp.async into a per-thread slot of a shared-memory staging area: the A stream is latency-bound (bytes in flight, not
-// bandwidth), and registers hold at most two k-blocks per thread.
-constexpr int WG_RAW_STAGES = 3, WG_LO_BUFS = 2, WG_A_DEPTH = 4;
-constexpr uint32_t WG_RAW_BYTES = 256 * 128, WG_A_BYTES = 128 * 128;
-constexpr size_t WG_SMEM_RAW = (size_t)(WG_RAW_STAGES + WG_LO_BUFS) * WG_RAW_BYTES + (size_t)WG_A_DEPTH * WG_A_BYTES + 1024 + 32 * 8 + 64;
+constexpr int WG_RAW_STAGES = 5, WG_LO_BUFS = 2;
+constexpr uint32_t WG_RAW_BYTES = 256 * 128;
+constexpr size_t WG_SMEM_RAW = (size_t)(WG_RAW_STAGES + WG_LO_BUFS) * WG_RAW_BYTES + 1024 + 32 * 8 + 64;
 static_assert(WG_SMEM_RAW <= 232448, "wgrad RAW ring exceeds the 227 KB of dynamic shared memory");
 constexpr int SEG_KB = 16;       // k-blocks (of 32 rows) accumulated in TMEM before the accumulator is drained (see flush)
 
@@ -85,8 +82,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   constexpr int NST = RAW ? WG_RAW_STAGES : S_STAGES;                  // B stages
   constexpr uint32_t STB = RAW ? WG_RAW_BYTES : STAGE_BYTES;           // bytes per B stage
   uint8_t* lobuf = smem + (size_t)NST * STB;                           // RAW only: WG_LO_BUFS derived lo tiles
-  uint8_t* astage = lobuf + (size_t)WG_LO_BUFS * WG_RAW_BYTES;         // RAW only: WG_A_DEPTH x [128 features][32 envs] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * STB + (RAW ? WG_LO_BUFS * WG_RAW_BYTES + WG_A_DEPTH * WG_A_BYTES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * STB + (RAW ? WG_LO_BUFS * WG_RAW_BYTES : 0));
   uint64_t* b_full = bars, *b_empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + A_SLOTS;
   uint64_t* enc_full = a_empty + A_SLOTS, *acc_full = enc_full + 1;
   uint64_t* acc_free = acc_full + 1;                                   // accumulator drained by the row threads (segment flush)
@@ -223,69 +219,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     };
     if (set < A_SETS) {
       // ---- A producers: columns [set * WA, set * WA + WA) of every k-block, loads issued one k-block ahead ------------
-      if constexpr (RAW) {
-        // global source of this thread's 16 floats of k-block q (nullptr: constant lane)
-        auto src_of = [&](int q) -> const float* {
-          const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
-          if (hs_agent >= 0) return k.h_seq + (((size_t)t * N_agents + hs_agent) * NH + hs_unit) * k.B + rb * 32 + set * WA;
-          if (real) return d.A + (((size_t)t * N_agents + i) * d.F_A + feat) * k.B + rb * 32 + set * WA;
-          return nullptr;
-        };
-        uint8_t* myslot = astage + (size_t)ka * 128 + set * (WA * 4);
-        auto issue = [&](int q) {                       // one commit group per k-block, also when nothing is copied
-          if (q < nkb) {
-            const float* src = src_of(q);
-            if (src != nullptr) {
-              uint8_t* dst = myslot + (size_t)(q % WG_A_DEPTH) * WG_A_BYTES;
-#pragma unroll
-              for (int p = 0; p < WA / 4; ++p) cp_async16(dst + 16 * p, src + 4 * p, 16);
-            }
-          }
-          cp_async_commit();
-        };
-        auto load_done = [&](int q, float (&dn)[WA]) {  // (1 - done) factors of the 16 envs (h^ rows only)
-          const int kb = kb0 + q, t = kb / bpt, rb = kb - t * bpt;
-          const float* p0 = k.done_pre + (size_t)t * k.B + rb * 32 + set * WA;
-#pragma unroll
-          for (int p = 0; p < WA / 4; ++p) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p0 + 4 * p));
-            dn[4 * p] = 1.0f - v.x; dn[4 * p + 1] = 1.0f - v.y; dn[4 * p + 2] = 1.0f - v.z; dn[4 * p + 3] = 1.0f - v.w;
-          }
-        };
-        float dn[WA];
-#pragma unroll
-        for (int j = 0; j < WA; ++j) dn[j] = 1.0f;
-        if (hs_mask && nkb > 0) load_done(0, dn);
-#pragma unroll
-        for (int q0 = 0; q0 < WG_A_DEPTH; ++q0) issue(q0);
-        for (int q = 0; q < nkb; ++q) {
-          cp_async_wait<WG_A_DEPTH - 1>();               // the group of k-block q has landed
-          float x[WA];
-          if (hs_agent >= 0 || real) {
-            const float4* sp4 = reinterpret_cast<const float4*>(myslot + (size_t)(q % WG_A_DEPTH) * WG_A_BYTES);
-#pragma unroll
-            for (int p = 0; p < WA / 4; ++p) {
-              const float4 v = sp4[p];
-              x[4 * p] = v.x * dn[4 * p]; x[4 * p + 1] = v.y * dn[4 * p + 1]; x[4 * p + 2] = v.z * dn[4 * p + 2]; x[4 * p + 3] = v.w * dn[4 * p + 3];
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < WA; ++j) x[j] = one ? 1.0f : 0.0f;
-          }
-          if (hs_mask && q + 1 < nkb) load_done(q + 1, dn);
-          produce_begin(c);
-#pragma unroll
-          for (int p = 0; p < WA / 8; ++p) {
-            float t8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = x[8 * p + j];
-            produce_piece(c, set * WA + 8 * p, t8);
-          }
-          produce_end(c);                                // (x has been consumed: the slot may be refilled)
-          issue(q + WG_A_DEPTH);
-          if ((q + 1) % SEG_KB == 0 || q + 1 == nkb) flush(q / SEG_KB);
-        }
-      } else {
       float xa[WA], xb[WA];                     // the operands of the next two k-blocks (two loads in flight per thread)
       auto emit_a = [&](int q, float (&x)[WA]) {
         produce_begin(c);
@@ -305,7 +238,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       for (int q = 0; q < nkb; q += 2) {
         emit_a(q, xa);
         if (q + 1 < nkb) emit_a(q + 1, xb);
-      }
       }
     } else {
       // ---- lo derivation (RAW tiles): lo = rn_tf32(x - trunc_tf32(x)) of the k-block's B stage ---------------------------
