@@ -311,11 +311,8 @@ def kernel_rooflines(env, model, vt, peaks, runner):
         pass
     per = traffic.get('per_kernel_bytes_per_launch', {})
 
-    def ncu_bytes(prefix):
-        for k, v in per.items():
-            if k.startswith(prefix):
-                return v
-        return None
+    def ncu_bytes(name):
+        return per.get(name)
 
     if not (e.use_tc and getattr(e, 'fuse_save', False)):
         # FFMA fallback: back-to-back launches of the p-call on one input
@@ -350,9 +347,10 @@ def kernel_rooflines(env, model, vt, peaks, runner):
     f_fwd, f_bwd, f_wg = issued_flops(lay, B, T)
     save_b = 3072                                          # SURVEY 8(d) "Backward": s, gates, c, h, pre-activations (~768 floats)
     var = '%d' % {'ia2c': 0, 'ma2c_nc': 1, 'ma2c_ic3': 2, 'ma2c_dial': 3}.get(e.variant, 1)
-    t_fwd = ncu_bytes('tc_cell_fwd_kernel<%s, 3' % var)
-    t_bwd = ncu_bytes('tc_cell_bwd_kernel<%s' % var)
-    t_wg = ncu_bytes('tc_wgrad_kernel')
+    # template arguments: forward <VAR, MODE_PS = 3, state_fm>, backward <VAR, state_fm, raw_tiles>, wgrad <raw_tiles>
+    t_fwd = ncu_bytes('tc_cell_fwd_kernel<%s, 3, %d>' % (var, int(e.state_fm)))
+    t_bwd = ncu_bytes('tc_cell_bwd_kernel<%s, %d, %d>' % (var, int(e.state_fm), int(e.raw_tiles)))
+    t_wg = ncu_bytes('tc_wgrad_kernel<%d>' % int(e.raw_tiles))
 
     def triple(alg_bytes, us, ncu_b, flops):
         ach = alg_bytes / (us * 1e-6) / 1e9
