@@ -145,3 +145,34 @@ def test_shipped_configs_equal_the_reference_configs():
         assert mine.read(os.path.join(ROOT, 'config', n)), 'missing ' + n
         ref.read(os.path.join(ref_dir, n))
         assert {s: dict(mine[s]) for s in mine.sections()} == {s: dict(ref[s]) for s in ref.sections()}, n
+
+
+def test_hetero_layout_embedding_round_trip():
+    """HeteroLayout: reference (tight) tensors <-> padded flat buffer.  Every tight element maps to its own
+    slot, everything else is zero except the policy-head bias of padded actions (-1e30), unpack(pack(x)) == x, names and
+    shapes follow the reference's *_hetero creation order (tests/golden/hetero_*.npz)."""
+    from deeprl_network_b200.layout import PI_PAD_BIAS, HeteroLayout
+    from helpers import golden, random_params
+    for agent in ('ma2c_nc', 'ma2c_ic3', 'ma2c_dial'):
+        g = golden('hetero_' + agent)
+        n_s, n_a = [int(x) for x in g['n_s_ls']], [int(x) for x in g['n_a_ls']]
+        lay = HeteroLayout(agent, n_s, n_a, g['mask'])
+        order = lay.creation_order()
+        assert [n for n, _ in order] == [str(n) for n in g['names']]
+        assert all(tuple(s) == tuple(g['w0shape/' + n]) for n, s in order)
+        params = random_params(order, seed=3)
+        flat = lay.pack(params)
+        back = lay.unpack(flat)
+        assert all(np.array_equal(back[n], params[n]) for n, _ in order)
+        used = np.concatenate([lay._idx[n] for n, _ in order])
+        assert len(used) == len(set(used.tolist())) == lay.n_real_param()
+        rest = np.ones(lay.n_param, bool); rest[used] = False
+        pad_bias = np.zeros(lay.n_param, bool); pad_bias[lay.pi_pad] = True
+        assert np.all(flat[rest & ~pad_bias] == 0) and np.all(flat[pad_bias] == np.float32(PI_PAD_BIAS))
+        assert len(lay.pi_pad) == sum(max(n_a) - a for a in n_a)
+        m = lay.c_model()
+        assert m.n_a == max(n_a) and m.agent[1].x_w == max(n_s) and m.agent[1].n_nbr == int(g['mask'][1].sum())
+        assert lay.kx_pad <= 32 and lay.kp_pad <= 32          # fits the tensor-core path's one-k-block encoders
+    with pytest.raises(NotImplementedError):
+        iso = np.zeros((3, 3), int); iso[0, 1] = iso[1, 0] = 1
+        HeteroLayout('ma2c_ic3', [5, 4, 3], [4, 3, 2], iso)   # CommNet agent without neighbours: mean over an empty set
