@@ -82,13 +82,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_bwd_kernel(const __grid
       float dv = 0.f;
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) if (cc == n_a) dv = dl[cc];
+      float4 vw[EW / 4];
+#pragma unroll
+      for (int q4 = 0; q4 < EW / 4; ++q4) vw[q4] = __ldg(reinterpret_cast<const float4*>(P + ag.o_v_w + e0) + q4);
 #pragma unroll
       for (int j = 0; j < EW; ++j) {
         float s = 0.f;
+        if (n_a == 4) {                       // one 16-byte (warp-uniform) load per hidden unit instead of four scalar ones
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(P + ag.o_pi_w) + e0 + j);
+          s = fmaf(dl[0], w4.x, s); s = fmaf(dl[1], w4.y, s); s = fmaf(dl[2], w4.z, s); s = fmaf(dl[3], w4.w, s);
+        } else {
 #pragma unroll
-        for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc)
-          if (cc < n_a) s = fmaf(dl[cc], __ldg(P + ag.o_pi_w + (e0 + j) * n_a + cc), s);
-        dh[j] = fmaf(dv, __ldg(P + ag.o_v_w + e0 + j), s);
+          for (int cc = 0; cc < NMARL_MAX_NA - 1; ++cc)
+            if (cc < n_a) s = fmaf(dl[cc], __ldg(P + ag.o_pi_w + (e0 + j) * n_a + cc), s);
+        }
+        dh[j] = fmaf(dv, f4get(vw[j >> 2], j & 3), s);
         dct[j] = 0.f;
       }
       if (k.has_next) {

@@ -110,13 +110,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
     const int e0 = set * EW;            // this thread's hidden units / encoder columns
 
     // ---- gather every encoder input of this thread up front (all loads in flight together) ------------------
+    const int inv_xw = 65536 / ag.x_w + 1, inv_na = 65536 / n_a + 1;    // exact floor(kk / d) for kk < 32, d <= 32
     float xv[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const int kk = c0 + j;
       float val = 0.f;
       if (kk < Kx) {
-        const int s = kk / ag.x_w, f = kk - s * ag.x_w;
+        const int s = (kk * inv_xw) >> 16, f = kk - s * ag.x_w;     // kk / x_w for kk < 32 without an integer division
         val = a.obs[((size_t)ag.x_src[s] * B + b) * m.obs_stride + f];
       }
       xv[j] = val;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_cell_fwd_kernel(const __grid
         const int kk = c0 + j;
         float val = 0.f;
         if (kk < Kp) {
-          const int s = kk / n_a, f = kk - s * n_a;
+          const int s = (kk * inv_na) >> 16, f = kk - s * n_a;
           val = a.fp[((size_t)ag.nbr[s] * B + b) * n_a + f];
         }
         pv[j] = val;

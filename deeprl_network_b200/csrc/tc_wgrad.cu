@@ -28,7 +28,7 @@ constexpr int WG_RAW_STAGES = 5, WG_LO_BUFS = 2;
 constexpr uint32_t WG_RAW_BYTES = 256 * 128;
 constexpr size_t WG_SMEM_RAW = (size_t)(WG_RAW_STAGES + WG_LO_BUFS) * WG_RAW_BYTES + 1024 + 32 * 8 + 64;
 static_assert(WG_SMEM_RAW <= 232448, "wgrad RAW ring exceeds the 227 KB of dynamic shared memory");
-constexpr int SEG_KB = 16;       // k-blocks (of 32 rows) accumulated in TMEM before the accumulator is drained (see flush)
+constexpr int SEG_KB = 20;       // k-blocks (of 32 rows) accumulated in TMEM before the accumulator is drained (see flush)
 
 struct TcWgK {
   int B, T, splits, ndp;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     // Segmented accumulation.  The tensor core adds every MMA into the fp32 accumulator with round-toward-zero: a bias
     // of ~2^-24 of the running sum per MMA that grows linearly with the chain length (measured 1.4e-4 of max|g| after
     // the 2 496 MMAs of one B = 4096, T = 60 split).  The accumulator is therefore drained every SEG_KB k-blocks
-    // (192 MMAs) and the segment sums are added up in registers / the CTA's own workspace slot with ordinary
+    // (240 MMAs at SEG_KB = 20) and the segment sums are added up in the CTA's own workspace slot with ordinary
     // round-to-nearest fp32 adds.
     const bool warp_active = quarter * 32 < d.ka_cnt + (d.ones ? 1 : 0) + d.p_cnt;   // tcgen05.ld is warp-collective
     float* out = wsj + ka;                                      // element (ka, n) of the partial block at out[n * 128]
