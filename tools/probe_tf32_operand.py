@@ -1,4 +1,6 @@
-"""Hardware probes for DESIGN.md 6.1 / 6.2, to run first thing on a B200:
+"""Hardware probes (run on a B200; result of round 2, session r2a: profiles/r2a_probe.txt -- both answers were "bit-identical"
+when the packed operands were still split by truncation.  The product now splits by round-to-nearest (tc.cuh), so (1)
+reports a small difference today: the raw tile is read truncated by the tensor core, the packed hi tile is rounded):
     python tools/probe_tf32_operand.py
 (1) Does the TF32 tensor-core datapath ignore the 13 low mantissa bits of a shared-memory operand?  The stand-alone
     3xTF32 GEMM runs with hi tile = masked values (what the product packs) and with hi tile = raw fp32 values; the
